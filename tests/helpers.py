@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests (oracle is the checker, never the product)."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["cells_default", "cells_nodensity", "cells_regs", "clusters", "cells_spatial"]
+REFERENCE_FILE = "/root/reference/tangram/mapping_optimizer.py"
+
+
+def load_golden(name):
+    """-> (ctor kwargs for a Mapper-like class, golden outputs dict)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    kw = {}
+    for k in z.files:
+        if k.startswith("in_"):
+            kw[k[3:]] = z[k]
+        elif k.startswith("hp_"):
+            kw[k[3:]] = float(z[k])
+    out = {k: z[k] for k in z.files if not (k.startswith("in_") or k.startswith("hp_"))}
+    if "d" not in kw:
+        kw["d"] = None
+    return kw, out
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def max_rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)))
+
+
+def load_reference_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_mapping_optimizer", REFERENCE_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
