@@ -1,0 +1,182 @@
+/*
+ * tangram_b200 -- C-ABI of the B200-native `map_cells_to_space` hot path.
+ *
+ * This is the drop-in boundary for ONE path of broadinstitute/Tangram: the optimizer in
+ * tangram/mapping_optimizer.py (class Mapper).  Each entry point cites the reference
+ * interface it replaces (file:line in the reference tree).  The library is plain C ABI:
+ * opaque handle, raw pointers and sizes, int status codes, no C++ / torch types, no
+ * exceptions, no exit().  Pointer arguments documented "host or device" are copied with
+ * cudaMemcpyDefault (UVA), mirroring the reference, which copies every input
+ * (`torch.tensor(ndarray)`, mapping_optimizer.py:83-157).
+ *
+ * Every function returns 0 on success or a negative tgb200_status; the message for the
+ * calling thread's last failure is available from tgb200_last_error().
+ *
+ * `stream` arguments are `cudaStream_t` passed as void* (NULL = legacy default stream).
+ */
+#ifndef TANGRAM_B200_H_
+#define TANGRAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TGB200_API __attribute__((visibility("default")))
+#else
+#define TGB200_API
+#endif
+
+typedef struct tgb200_mapper tgb200_mapper; /* opaque; replaces a `Mapper` instance */
+
+typedef enum tgb200_status {
+  TGB200_OK = 0,
+  TGB200_ERR_INVALID = -1,   /* bad argument / bad config                              */
+  TGB200_ERR_CUDA = -2,      /* CUDA runtime / driver error (message has the detail)   */
+  TGB200_ERR_STATE = -3,     /* call order violated (e.g. run before set_expression)   */
+  TGB200_ERR_UNSUPPORTED = -4, /* term outside the hot-path scope (Moran / Geary)      */
+  TGB200_ERR_NO_DEVICE = -5  /* no sm_100 device: there is NO CPU fallback             */
+} tgb200_status;
+
+/* Arithmetic of the two contractions (softmax(M)^T S and S dY^T). */
+typedef enum tgb200_precision {
+  TGB200_PREC_FP32 = 0,  /* fp32 FFMA contraction: parity mode (reference is fp32, TF32 off) */
+  TGB200_PREC_BF16 = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
+} tgb200_precision;
+
+/* mapping_optimizer.py:212-221: which density term is active. */
+typedef enum tgb200_density_mode {
+  TGB200_DENSITY_NONE = 0,   /* d is None                       (:220-221)            */
+  TGB200_DENSITY_CELLS = 1,  /* d_pred = log(P.sum(0)/N)        (:217)                */
+  TGB200_DENSITY_SOURCE = 2  /* d_pred = log(d_source @ P)      (:215, clusters mode) */
+} tgb200_density_mode;
+
+/* Sparse V x V operators (CSR) that replace the reference's dense V x V matrices. */
+typedef enum tgb200_graph {
+  TGB200_GRAPH_VOXEL_WEIGHTS = 0,       /* Mapper(voxel_weights=)        :125-127, used :235-236 */
+  TGB200_GRAPH_NEIGHBORHOOD_FILTER = 1, /* Mapper(neighborhood_filter=)  :130-132, used :244     */
+  TGB200_GRAPH_SPATIAL_WEIGHTS = 2      /* Mapper(spatial_weights=)      :139-141, used :171     */
+} tgb200_graph;
+
+/* Columns of one history row (one row per epoch; loss BEFORE that epoch's update,
+ * mapping_optimizer.py:383-392).  Terms whose lambda is 0 are NaN, as in the reference
+ * (:208-263: x / lambda with lambda == 0). */
+enum {
+  TGB200_HIST_TOTAL = 0,   /* total_loss            :266-270 */
+  TGB200_HIST_MAIN = 1,    /* main_loss  (gv/l_g1)  :208     */
+  TGB200_HIST_VG = 2,      /* vg_reg                :209     */
+  TGB200_HIST_KL = 3,      /* kl_reg                :219     */
+  TGB200_HIST_ENTROPY = 4, /* entropy_reg           :225     */
+  TGB200_HIST_L1 = 5,      /* l1_reg                :229     */
+  TGB200_HIST_L2 = 6,      /* l2_reg                :231     */
+  TGB200_HIST_NEIGHBORHOOD = 7, /* gv_neighborhood_sim :237  */
+  TGB200_HIST_CT_ISLANDS = 8,   /* ct_island_penalty   :246  */
+  TGB200_HIST_GETIS_ORD = 9,    /* getis_ord_sim       :257  */
+  TGB200_HIST_COLS = 16
+};
+
+/* Replaces the keyword arguments of Mapper.__init__ (mapping_optimizer.py:19-45). */
+typedef struct tgb200_config {
+  int32_t struct_size;     /* = sizeof(tgb200_config); ABI guard                              */
+  int32_t device;          /* CUDA device ordinal                                             */
+  int32_t n_cells;         /* rows of M / S held by THIS handle (S.shape[0], :150)            */
+  int32_t n_voxels;        /* G.shape[0]                                                      */
+  int32_t n_genes;         /* training genes (S.shape[1] == G.shape[1])                       */
+  int32_t n_types;         /* ct_encode.shape[1], 0 if unused (:134-136)                      */
+  int64_t n_cells_global;  /* total cells over all ranks (== n_cells when not sharded)        */
+  int32_t precision;       /* tgb200_precision                                                */
+  int32_t density_mode;    /* tgb200_density_mode                                             */
+  float lambda_g1;         /* :27  */
+  float lambda_d;          /* :28  */
+  float lambda_g2;         /* :29  */
+  float lambda_r;          /* :30  */
+  float lambda_l1;         /* :31  */
+  float lambda_l2;         /* :32  */
+  float lambda_neighborhood_g1; /* :33 */
+  float lambda_ct_islands; /* :40  */
+  float lambda_getis_ord;  /* :35  */
+  float adam_beta1;        /* torch.optim.Adam defaults used at :373 -> 0.9   */
+  float adam_beta2;        /* 0.999 */
+  float adam_eps;          /* 1e-8  */
+} tgb200_config;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+
+/* Mapper.__init__ (:19-157) minus the data: allocates device state for the given shape. */
+TGB200_API int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out);
+TGB200_API int tgb200_destroy(tgb200_mapper* h);
+
+/* ---- inputs (copied; caller keeps ownership) ---------------------------------------- */
+
+/* S (n_cells x n_genes) and G (n_voxels x n_genes), row-major f32, host or device.
+ * Replaces :83-92 (self.S / self.G / S_train / G_train). */
+TGB200_API int tgb200_set_expression(tgb200_mapper* h, const float* S, const float* G, void* stream);
+/* d (n_voxels) and optional d_source (n_cells), :114-120.  NULL = absent. */
+TGB200_API int tgb200_set_density(tgb200_mapper* h, const float* d, const float* d_source, void* stream);
+/* ct_encode (n_cells x n_types) one-hot, :134-136. */
+TGB200_API int tgb200_set_ct_encode(tgb200_mapper* h, const float* ct_encode, void* stream);
+/* One V x V operator as CSR with HOST pointers (int32 indptr[V+1], indices[nnz], f32 values[nnz]).
+ * Replaces the dense matrices at :125-141 (built by tangram/spatial_weights.py:5-30). */
+TGB200_API int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indptr,
+                                const int32_t* indices, const float* values, int64_t nnz, void* stream);
+
+/* Initial mapping M0 (n_cells x n_voxels f32, host or device): the float32 cast of the
+ * reference's host draw at :147-157.  Resets the Adam state and the step counter. */
+TGB200_API int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* stream);
+/* Device-side N(0,1) init (Philox) for throughput runs; NOT bit-compatible with :150. */
+TGB200_API int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream);
+
+/* ---- the hot loop ------------------------------------------------------------------ */
+
+/* Mapper.train's loop body x n_steps (:382-396): loss, backward, Adam.  No host syncs;
+ * per-epoch scalars go to a device-side history buffer. */
+TGB200_API int tgb200_run(tgb200_mapper* h, int32_t n_steps, float learning_rate, void* stream);
+
+/* Cell-sharded operation (one handle per rank): step_begin computes this rank's partial
+ * sums; the caller all-reduces (sum) the exchange buffer across ranks (NCCL); step_end
+ * finishes the iteration.  tgb200_run == step_begin + step_end when not sharded. */
+TGB200_API int tgb200_step_begin(tgb200_mapper* h, void* stream);
+TGB200_API int tgb200_exchange_buffer(tgb200_mapper* h, float** device_ptr, int64_t* n_floats);
+TGB200_API int tgb200_step_end(tgb200_mapper* h, float learning_rate, void* stream);
+
+/* ---- outputs ----------------------------------------------------------------------- */
+
+/* Number of epochs recorded so far. */
+TGB200_API int tgb200_history_len(tgb200_mapper* h, int64_t* n);
+/* Rows [first, first+count) of the history, TGB200_HIST_COLS floats each, to HOST memory.
+ * Replaces the per-iteration .tolist() syncs at :208-263 / :390-392. */
+TGB200_API int tgb200_get_history(tgb200_mapper* h, int64_t first, int64_t count, float* out_host, void* stream);
+/* softmax(M, dim=1) as n_cells x n_voxels f32 (host or device).  Replaces :406-408. */
+TGB200_API int tgb200_get_mapping(tgb200_mapper* h, float* out, void* stream);
+/* _val_loss_fn (:311-356): out[4] = expression_sim, gv_sim, sp_sparsity_weighted_gv_sim, entropy (HOST). */
+TGB200_API int tgb200_validation_terms(tgb200_mapper* h, float* out4_host, void* stream);
+/* project_genes' GEMM (tangram/utils.py:368): out (n_voxels x n_cols) = softmax(M)^T X,
+ * X (n_cells x n_cols) row-major f32, host or device; fp32 accumulate. */
+TGB200_API int tgb200_project(tgb200_mapper* h, const float* X, int64_t n_cols, float* out, void* stream);
+
+/* Checkpoint / resume (the reference stubs this: `raise NotImplemented`, :151-153).
+ * Any pointer may be NULL to skip it.  M, m, v: n_cells x n_voxels f32, host or device. */
+TGB200_API int tgb200_get_state(tgb200_mapper* h, float* M, float* m, float* v, int64_t* step, void* stream);
+TGB200_API int tgb200_set_state(tgb200_mapper* h, const float* M, const float* m, const float* v, int64_t step, void* stream);
+
+/* ---- introspection ----------------------------------------------------------------- */
+
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
+TGB200_API int tgb200_kernel_launches(tgb200_mapper* h, int64_t* n);
+/* Runs ONE full iteration with CUDA events around each kernel on `stream`;
+ * fills names[i] (static strings) / ms[i] for up to `cap` kernels, *n = count. */
+TGB200_API int tgb200_profile_step(tgb200_mapper* h, float learning_rate, void* stream,
+                                   const char** names, float* ms, int32_t cap, int32_t* n);
+/* Algorithmic bytes and flops of one iteration for this handle's shape. */
+TGB200_API int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops);
+
+TGB200_API const char* tgb200_last_error(void);
+TGB200_API const char* tgb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TANGRAM_B200_H_ */

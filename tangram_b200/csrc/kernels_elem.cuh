@@ -1,0 +1,538 @@
+// Bandwidth-bound kernels of the hot path: row softmax + statistics, loss reductions,
+// loss scalars, dY assembly.  Coalesced float4 HBM loads + warp-shuffle reductions.
+// Reference: tangram/mapping_optimizer.py:189-309 (_loss_fn).
+#pragma once
+#include "common.cuh"
+#include <curand_kernel.h>
+
+namespace tgb {
+
+// ------------------------------------------------------------------------------------
+// Row pass: P = softmax(M, dim=1) (:201) + per-row statistics.
+// One CTA per cell row; the row lives in registers (ITEMS float4 per thread) when it fits,
+// otherwise it is re-read (L2-resident).  Also emits sum_j P log P (entropy, :224),
+// sum|M| and sum M^2 (:228-231) when those terms are enabled.
+// Pad columns [V, ldp) of P are written as zero so the GEMMs can read whole vectors.
+// ------------------------------------------------------------------------------------
+template <typename PT>
+__device__ __forceinline__ void store_p4(PT* dst, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_p4<float>(float* dst, float a, float b, float c, float d) {
+  st_stream(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
+}
+template <>
+__device__ __forceinline__ void store_p4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+template <typename PT, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, int ldp,
+               RowStat* __restrict__ stats, float* __restrict__ rowaux /* [N][2] or null */,
+               int want_entropy) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x;
+  const float* mrow = M + (size_t)row * ldm;
+  const int nvec = ldp >> 2;  // float4 slots incl. pad (ldm == ldp)
+  constexpr bool kCached = ITEMS > 0;
+  constexpr int NI = kCached ? ITEMS : 1;
+  float4 x[NI];
+
+  float mx = -INFINITY, s1 = 0.f, s2 = 0.f;
+  auto visit_max = [&](const float4& v, int c) {
+    if (c + 0 < V) { mx = fmaxf(mx, v.x); s1 += fabsf(v.x); s2 += v.x * v.x; }
+    if (c + 1 < V) { mx = fmaxf(mx, v.y); s1 += fabsf(v.y); s2 += v.y * v.y; }
+    if (c + 2 < V) { mx = fmaxf(mx, v.z); s1 += fabsf(v.z); s2 += v.z * v.z; }
+    if (c + 3 < V) { mx = fmaxf(mx, v.w); s1 += fabsf(v.w); s2 += v.w * v.w; }
+  };
+  if (kCached) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = threadIdx.x + i * THREADS;
+      x[i] = (q < nvec) ? ld_stream(reinterpret_cast<const float4*>(mrow) + q) : make_float4(0, 0, 0, 0);
+      if (q < nvec) visit_max(x[i], q * 4);
+    }
+  } else {
+    for (int q = threadIdx.x; q < nvec; q += THREADS)
+      visit_max(reinterpret_cast<const float4*>(mrow)[q], q * 4);
+  }
+  mx = block_reduce<true>(mx, sh);
+
+  float z = 0.f;
+  auto visit_sum = [&](const float4& v, int c) {
+    if (c + 0 < V) z += expf(v.x - mx);
+    if (c + 1 < V) z += expf(v.y - mx);
+    if (c + 2 < V) z += expf(v.z - mx);
+    if (c + 3 < V) z += expf(v.w - mx);
+  };
+  if (kCached) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = threadIdx.x + i * THREADS;
+      if (q < nvec) visit_sum(x[i], q * 4);
+    }
+  } else {
+    for (int q = threadIdx.x; q < nvec; q += THREADS)
+      visit_sum(reinterpret_cast<const float4*>(mrow)[q], q * 4);
+  }
+  z = block_reduce<false>(z, sh);
+
+  RowStat st;
+  st.mx = mx;
+  st.inv_z = 1.0f / z;
+  st.log_z = logf(z);
+  st.h = 0.f;
+
+  float h = 0.f;
+  PT* prow = P + (size_t)row * ldp;
+  auto emit = [&](const float4& v, int q) {
+    const int c = q * 4;
+    float p0 = (c + 0 < V) ? softmax_prob(v.x, st) : 0.f;
+    float p1 = (c + 1 < V) ? softmax_prob(v.y, st) : 0.f;
+    float p2 = (c + 2 < V) ? softmax_prob(v.z, st) : 0.f;
+    float p3 = (c + 3 < V) ? softmax_prob(v.w, st) : 0.f;
+    if (want_entropy) {
+      if (c + 0 < V) h += p0 * ((v.x - mx) - st.log_z);
+      if (c + 1 < V) h += p1 * ((v.y - mx) - st.log_z);
+      if (c + 2 < V) h += p2 * ((v.z - mx) - st.log_z);
+      if (c + 3 < V) h += p3 * ((v.w - mx) - st.log_z);
+    }
+    store_p4<PT>(prow + c, p0, p1, p2, p3);
+  };
+  if (kCached) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = threadIdx.x + i * THREADS;
+      if (q < nvec) emit(x[i], q);
+    }
+  } else {
+    for (int q = threadIdx.x; q < nvec; q += THREADS)
+      emit(reinterpret_cast<const float4*>(mrow)[q], q);
+  }
+  if (want_entropy) h = block_reduce<false>(h, sh);
+  if (rowaux != nullptr) {
+    s1 = block_reduce<false>(s1, sh);
+    s2 = block_reduce<false>(s2, sh);
+  }
+  if (threadIdx.x == 0) {
+    st.h = h;
+    stats[row] = st;
+    if (rowaux != nullptr) { rowaux[2 * row] = s1; rowaux[2 * row + 1] = s2; }
+  }
+}
+
+// Sum of per-row scalars (entropy, L1, L2) over this rank's rows -> 4-float tail of the
+// exchange buffer.  Deterministic (fixed tree), one CTA.
+__global__ void __launch_bounds__(1024)
+k_row_scalar_reduce(const RowStat* __restrict__ stats, const float* __restrict__ rowaux, int n_rows,
+                    float* __restrict__ tail) {
+  __shared__ float sh[32];
+  float h = 0.f, a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+    h += stats[i].h;
+    if (rowaux) { a += rowaux[2 * i]; b += rowaux[2 * i + 1]; }
+  }
+  h = block_reduce<false>(h, sh);
+  a = block_reduce<false>(a, sh);
+  b = block_reduce<false>(b, sh);
+  if (threadIdx.x == 0) { tail[0] = h; tail[1] = a; tail[2] = b; tail[3] = 0.f; }
+}
+
+// ------------------------------------------------------------------------------------
+// Loss stage.  All of it lives on V x Ke data (tiny next to N x V).
+// ------------------------------------------------------------------------------------
+struct Csr {
+  const int* indptr;
+  const int* indices;
+  const float* vals;
+};
+
+constexpr int kLossRows = 64;   // voxel rows per CTA in the reduction kernels
+constexpr int kLossCols = 128;  // gene columns per CTA (= threads)
+
+struct LossParams {
+  int V, K, Ke, T, ct_off, density_mode;
+  long long n_cells_global;
+  float lam_g1, lam_d, lam_g2, lam_r, lam_l1, lam_l2, lam_nb, lam_ct, lam_go;
+  const float* G;     // V x Ke, zero beyond K
+  const float* d;     // V
+  float* Y;           // V x Ke (+4 tail floats): predicted expression | density cols | ct cols
+  const float* ngc;   // K   max(||G_.k||, eps)
+  const float* ngr;   // V   max(||G_j.||, eps)
+  Csr W, WT, F, FT, A, AT;
+  const float* WG;    // V x Ke   W @ G   (constant, :236 recomputes it every iteration)
+  const float* nwg;   // K
+  const float* AG;    // V x Ke   (A+I) @ G
+  const float* nag;   // K
+  const float* sgnG;  // K   sign(colsum G)
+  float* Z;           // V x Ke   W @ Y
+  float* Zg;          // V x Ke   (A+I) @ Y
+  float* H;           // V x T    1[R > 0]
+  float* colpart;     // [nchunk][3][Ke]
+  float* colpart_nb;  // [nchunk][2][Ke]
+  float* colpart_go;  // [nchunk][2][Ke]
+  float* rowpart;     // [ncolchunk][V][2]
+  float* ctpart;      // [n ct blocks]
+  int n_ct_blocks;
+  float* coefA; float* coefB;     // Ke
+  float* coefAn; float* coefBn;   // Ke
+  float* coefAg; float* coefBg;   // Ke
+  float* coefAr; float* coefBr;   // V
+  float* densg;                   // V
+};
+
+// Y = sum over split partials; per-gene <Y,G>, |Y|^2, colsum(Y) for this row chunk;
+// per-voxel <Y,G>, |Y|^2 for this column chunk (only when lambda_g2 != 0).
+__global__ void __launch_bounds__(kLossCols)
+k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_stats) {
+  __shared__ float shr[4][kLossRows][2];
+  const int k = blockIdx.x * kLossCols + threadIdx.x;
+  const int j0 = blockIdx.y * kLossRows;
+  const size_t plane = (size_t)p.V * p.Ke;
+  const bool in = k < p.Ke, gene = k < p.K;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float dot = 0.f, ny2 = 0.f, ys = 0.f;
+  for (int r = 0; r < kLossRows; ++r) {
+    const int j = j0 + r;
+    if (j >= p.V) break;   // uniform across the CTA
+    float y = 0.f, g = 0.f;
+    if (in) {
+      const size_t o = (size_t)j * p.Ke + k;
+      for (int z = 0; z < nsplit; ++z) y += part[z * plane + o];
+      if (nsplit > 1 || part != p.Y) p.Y[o] = y;
+      if (gene) { g = p.G[o]; dot += y * g; ny2 += y * y; ys += y; }
+    }
+    if (row_stats) {
+      float a = gene ? y * g : 0.f, b = gene ? y * y : 0.f;
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) { shr[wid][r][0] = a; shr[wid][r][1] = b; }
+    }
+  }
+  if (in) {
+    float* cp = p.colpart + (size_t)blockIdx.y * 3 * p.Ke;
+    cp[k] = dot; cp[p.Ke + k] = ny2; cp[2 * p.Ke + k] = ys;
+  }
+  if (row_stats) {
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < kLossRows && j0 + r < p.V) {
+      float a = shr[0][r][0] + shr[1][r][0] + shr[2][r][0] + shr[3][r][0];
+      float b = shr[0][r][1] + shr[1][r][1] + shr[2][r][1] + shr[3][r][1];
+      float* rp = p.rowpart + ((size_t)blockIdx.x * p.V + (j0 + r)) * 2;
+      rp[0] = a; rp[1] = b;
+    }
+  }
+}
+
+// Zout = Op @ Y (CSR, ~7 nnz/row) fused with the per-gene <Zout,REF>, |Zout|^2 partials.
+// Replaces the dense (V x V) @ (V x K) SGEMMs at :235 and :171.
+__global__ void __launch_bounds__(kLossCols)
+k_spatial_colstats(int V, int K, int Ke, Csr op, const float* __restrict__ Y, const float* __restrict__ REF,
+                   float* __restrict__ Zout, float* __restrict__ colpart2) {
+  const int k = blockIdx.x * kLossCols + threadIdx.x;
+  const int j0 = blockIdx.y * kLossRows;
+  const bool gene = k < K;
+  float dot = 0.f, nz2 = 0.f;
+  for (int r = 0; r < kLossRows; ++r) {
+    const int j = j0 + r;
+    if (j >= V) break;
+    if (gene) {
+      float z = 0.f;
+      for (int e = op.indptr[j]; e < op.indptr[j + 1]; ++e)
+        z += op.vals[e] * Y[(size_t)op.indices[e] * Ke + k];
+      const size_t o = (size_t)j * Ke + k;
+      Zout[o] = z;
+      dot += z * REF[o];
+      nz2 += z * z;
+    }
+  }
+  if (k < Ke) {
+    float* cp = colpart2 + (size_t)blockIdx.y * 2 * Ke;
+    cp[k] = dot; cp[Ke + k] = nz2;
+  }
+}
+
+// Cell-type islands (:242-248): R = C - F C, hinge partial sums and H = 1[R > 0].
+__global__ void __launch_bounds__(256)
+k_ct_islands(LossParams p) {
+  __shared__ float sh[32];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float hinge = 0.f;
+  if (idx < (long long)p.V * p.T) {
+    const int j = (int)(idx / p.T), t = (int)(idx % p.T);
+    const float c = p.Y[(size_t)j * p.Ke + p.ct_off + t];
+    float fc = 0.f;
+    for (int e = p.F.indptr[j]; e < p.F.indptr[j + 1]; ++e)
+      fc += p.F.vals[e] * p.Y[(size_t)p.F.indices[e] * p.Ke + p.ct_off + t];
+    const float R = c - fc;
+    hinge = fmaxf(R, 0.f);
+    p.H[idx] = R > 0.f ? 1.f : 0.f;
+  }
+  hinge = block_reduce<false>(hinge, sh);
+  if (threadIdx.x == 0) p.ctpart[blockIdx.x] = hinge;
+}
+
+// One CTA: finishes every reduction, writes the history row and the dY coefficients.
+// cos(x,y) = <x,y> / (max(|x|,eps) max(|y|,eps))   (torch semantics, :205-206)
+// d mean_k cos / dY_jk = a_k G_jk - b_k Y_jk,  a_k = 1/(K ny ng),  b_k = cos_k/(K ny^2)
+__global__ void __launch_bounds__(1024)
+k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist_row) {
+  __shared__ float sh[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float nan = __int_as_float(0x7fc00000);
+  float gv = 0.f, nb = 0.f, go = 0.f;
+  for (int k = tid; k < p.K; k += nt) {
+    float dot = 0.f, ny2 = 0.f, ys = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const float* cp = p.colpart + (size_t)c * 3 * p.Ke;
+      dot += cp[k]; ny2 += cp[p.Ke + k]; ys += cp[2 * p.Ke + k];
+    }
+    const float ny = fmaxf(sqrtf(ny2), kCosEps), ng = p.ngc[k];
+    const float cs = dot / (ny * ng);
+    gv += cs;
+    p.coefA[k] = p.lam_g1 / ((float)p.K * ny * ng);
+    p.coefB[k] = p.lam_g1 * cs / ((float)p.K * ny * ny);
+    if (p.lam_nb > 0.f) {
+      float d2 = 0.f, n2 = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        const float* cp = p.colpart_nb + (size_t)c * 2 * p.Ke;
+        d2 += cp[k]; n2 += cp[p.Ke + k];
+      }
+      const float nz = fmaxf(sqrtf(n2), kCosEps), nr = p.nwg[k];
+      const float c2 = d2 / (nz * nr);
+      nb += c2;
+      p.coefAn[k] = p.lam_nb / ((float)p.K * nz * nr);
+      p.coefBn[k] = p.lam_nb * c2 / ((float)p.K * nz * nz);
+    }
+    if (p.lam_go > 0.f) {
+      // cos(G*(G), G*(Y)) with G*(X) = (A+I) X / colsum(X)  (:171): the per-gene scale
+      // cancels in the cosine up to its sign, so only sign(colsum) survives.
+      float d2 = 0.f, n2 = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        const float* cp = p.colpart_go + (size_t)c * 2 * p.Ke;
+        d2 += cp[k]; n2 += cp[p.Ke + k];
+      }
+      const float sgn = ((ys > 0.f) ? 1.f : -1.f) * p.sgnG[k];
+      const float nz = fmaxf(sqrtf(n2), kCosEps), nr = p.nag[k];
+      const float c2 = d2 / (nz * nr);
+      go += sgn * c2;
+      p.coefAg[k] = sgn * p.lam_go / ((float)p.K * nz * nr);
+      p.coefBg[k] = sgn * p.lam_go * c2 / ((float)p.K * nz * nz);
+    }
+  }
+  gv = block_reduce<false>(gv, sh) / (float)p.K;
+  nb = block_reduce<false>(nb, sh) / (float)p.K;
+  go = block_reduce<false>(go, sh) / (float)p.K;
+
+  float vg = 0.f;
+  if (p.lam_g2 != 0.f) {
+    for (int j = tid; j < p.V; j += nt) {
+      float dot = 0.f, ny2 = 0.f;
+      for (int c = 0; c < ncolchunk; ++c) {
+        const float* rp = p.rowpart + ((size_t)c * p.V + j) * 2;
+        dot += rp[0]; ny2 += rp[1];
+      }
+      const float ny = fmaxf(sqrtf(ny2), kCosEps), ng = p.ngr[j];
+      const float cs = dot / (ny * ng);
+      vg += cs;
+      p.coefAr[j] = p.lam_g2 / ((float)p.V * ny * ng);
+      p.coefBr[j] = p.lam_g2 * cs / ((float)p.V * ny * ny);
+    }
+    vg = block_reduce<false>(vg, sh) / (float)p.V;
+  }
+
+  // density KL (:212-221): KLDivLoss(sum)(log dhat, d) = sum xlogy(d,d) - d log dhat
+  float kl = 0.f;
+  if (p.density_mode != 0) {
+    for (int j = tid; j < p.V; j += nt) {
+      const float cs = p.Y[(size_t)j * p.Ke + p.K] + p.Y[(size_t)j * p.Ke + p.K + 1];
+      const float dhat = (p.density_mode == 1) ? cs / (float)p.n_cells_global : cs;
+      const float dj = p.d[j];
+      kl += ((dj > 0.f) ? dj * logf(dj) : 0.f) - dj * logf(dhat);
+      p.densg[j] = -p.lam_d * dj / cs;
+    }
+    kl = block_reduce<false>(kl, sh);
+  }
+
+  float ct = 0.f;
+  if (p.lam_ct > 0.f) {
+    for (int b = tid; b < p.n_ct_blocks; b += nt) ct += p.ctpart[b];
+    ct = block_reduce<false>(ct, sh) / ((float)p.V * (float)p.T);
+  }
+
+  if (tid == 0) {
+    const float* tail = p.Y + (size_t)p.V * p.Ke;
+    const float ent = -tail[0], l1 = tail[1], l2 = tail[2];
+    float total = -p.lam_g1 * gv;
+    if (p.lam_g2 != 0.f) total -= p.lam_g2 * vg;
+    if (p.density_mode != 0) total += p.lam_d * kl;
+    if (p.lam_r != 0.f) total += p.lam_r * ent;
+    if (p.lam_l1 != 0.f) total += p.lam_l1 * l1;
+    if (p.lam_l2 != 0.f) total += p.lam_l2 * l2;
+    if (p.lam_ct > 0.f) total += p.lam_ct * ct;
+    if (p.lam_nb > 0.f) total -= p.lam_nb * nb;
+    if (p.lam_go > 0.f) total -= p.lam_go * go;
+    hist_row[0] = total;
+    hist_row[1] = gv;
+    hist_row[2] = (p.lam_g2 != 0.f) ? vg : nan;
+    hist_row[3] = (p.density_mode != 0 && p.lam_d != 0.f) ? kl : nan;
+    hist_row[4] = (p.lam_r != 0.f) ? ent : nan;
+    hist_row[5] = (p.lam_l1 != 0.f) ? l1 : nan;
+    hist_row[6] = (p.lam_l2 != 0.f) ? l2 : nan;
+    hist_row[7] = (p.lam_nb > 0.f) ? nb : nan;
+    hist_row[8] = (p.lam_ct > 0.f) ? ct : nan;
+    hist_row[9] = (p.lam_go > 0.f) ? go : nan;
+    for (int i = 10; i < 16; ++i) hist_row[i] = 0.f;
+  }
+}
+
+// dY_ext = dL/dY_ext (V x Ke): gene columns from the cosine terms (+ transposed SpMM of
+// the spatial terms), density columns, cell-type columns.  Written in f32 and, for the
+// tensor-core path, bf16.
+__global__ void __launch_bounds__(kLossCols)
+k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ dYb) {
+  const int k = blockIdx.x * kLossCols + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= p.Ke) return;
+  const size_t o = (size_t)j * p.Ke + k;
+  float dy = 0.f;
+  if (k < p.K) {
+    const float y = p.Y[o], g = p.G[o];
+    dy = -(p.coefA[k] * g - p.coefB[k] * y);
+    if (p.lam_g2 != 0.f) dy -= p.coefAr[j] * g - p.coefBr[j] * y;
+    if (p.lam_nb > 0.f) {
+      const float a = p.coefAn[k], b = p.coefBn[k];
+      float acc = 0.f;
+      for (int e = p.WT.indptr[j]; e < p.WT.indptr[j + 1]; ++e) {
+        const size_t q = (size_t)p.WT.indices[e] * p.Ke + k;
+        acc += p.WT.vals[e] * (a * p.WG[q] - b * p.Z[q]);
+      }
+      dy -= acc;
+    }
+    if (p.lam_go > 0.f) {
+      const float a = p.coefAg[k], b = p.coefBg[k];
+      float acc = 0.f;
+      for (int e = p.AT.indptr[j]; e < p.AT.indptr[j + 1]; ++e) {
+        const size_t q = (size_t)p.AT.indices[e] * p.Ke + k;
+        acc += p.AT.vals[e] * (a * p.AG[q] - b * p.Zg[q]);
+      }
+      dy -= acc;
+    }
+  } else if (k < p.K + 2) {
+    dy = (p.density_mode != 0) ? p.densg[j] : 0.f;
+  } else if (k < p.ct_off + p.T && p.lam_ct > 0.f) {
+    const int t = k - p.ct_off;
+    float acc = p.H[(size_t)j * p.T + t];
+    for (int e = p.FT.indptr[j]; e < p.FT.indptr[j + 1]; ++e)
+      acc -= p.FT.vals[e] * p.H[(size_t)p.FT.indices[e] * p.T + t];
+    dy = p.lam_ct * acc / ((float)p.V * (float)p.T);
+  }
+  dY[o] = dy;
+  if (dYb != nullptr) dYb[o] = __float2bfloat16_rn(dy);
+}
+
+// ------------------------------------------------------------------------------------
+// One-time helpers (constants of the loss, input packing, init).
+// ------------------------------------------------------------------------------------
+__global__ void k_spmm(int V, int K, int Ke, Csr op, const float* __restrict__ X, float* __restrict__ Z) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= Ke) return;
+  float z = 0.f;
+  if (k < K)
+    for (int e = op.indptr[j]; e < op.indptr[j + 1]; ++e) z += op.vals[e] * X[(size_t)op.indices[e] * Ke + k];
+  Z[(size_t)j * Ke + k] = z;
+}
+
+// per-column clamped norm + sign of the column sum (thread per column)
+__global__ void k_col_norms(int V, int K, int Ke, const float* __restrict__ X, float* __restrict__ nrm,
+                            float* __restrict__ sgn) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s2 = 0.f, s = 0.f;
+  for (int j = 0; j < V; ++j) { const float x = X[(size_t)j * Ke + k]; s2 += x * x; s += x; }
+  nrm[k] = fmaxf(sqrtf(s2), kCosEps);
+  if (sgn) sgn[k] = s > 0.f ? 1.f : -1.f;
+}
+// per-row clamped norm over the K gene columns (warp per row)
+__global__ void k_row_norms(int V, int K, int Ke, const float* __restrict__ X, float* __restrict__ nrm) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= V) return;
+  float s2 = 0.f;
+  for (int k = threadIdx.x & 31; k < K; k += 32) { const float x = X[(size_t)j * Ke + k]; s2 += x * x; }
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) nrm[j] = fmaxf(sqrtf(s2), kCosEps);
+}
+
+// dst[r][0:cols] = src[r][0:cols] (dense, ld = cols) into a padded row-major buffer; pad untouched
+__global__ void k_pack_rows(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst, int ld,
+                            int col_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[(size_t)r * ld + col_off + c] = src[i];
+}
+__global__ void k_unpack_rows(const float* __restrict__ src, int ld, int rows, int cols, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[i] = src[(size_t)r * ld + c];
+}
+// density columns of S_ext: cells mode (1, 0); clusters mode (w, 0) in fp32 or (hi, lo) split for bf16
+__global__ void k_fill_density_cols(float* __restrict__ Sx, int rows, int ld, int col, const float* __restrict__ w,
+                                    int split_bf16) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float a = 1.f, b = 0.f;
+  if (w != nullptr) {
+    a = w[r];
+    if (split_bf16) {
+      const float hi = __bfloat162float(__float2bfloat16_rn(a));
+      b = a - hi; a = hi;
+    }
+  }
+  Sx[(size_t)r * ld + col] = a;
+  Sx[(size_t)r * ld + col + 1] = b;
+}
+__global__ void k_f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+// M0 ~ N(0,1) on device (Philox4x32-10), pad columns zero.  Throughput runs only; the
+// reference draw (:150) is a host MT19937 float64 draw and is uploaded via set_mapping.
+__global__ void k_init_normal(float* __restrict__ M, int rows, int V, int ld, unsigned long long seed) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 each
+  const int nvec = ld >> 2;
+  if (q >= (long long)rows * nvec) return;
+  const int r = (int)(q / nvec), c = (int)(q % nvec) * 4;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)q, 0, &st);
+  float4 n = curand_normal4(&st);
+  if (c + 0 >= V) n.x = 0.f;
+  if (c + 1 >= V) n.y = 0.f;
+  if (c + 2 >= V) n.z = 0.f;
+  if (c + 3 >= V) n.w = 0.f;
+  reinterpret_cast<float4*>(M + (size_t)r * ld)[c >> 2] = n;
+}
+// out = sum of `nplanes` partial planes (deterministic order); used before the NCCL exchange
+__global__ void k_sum_planes(const float* __restrict__ part, int nplanes, size_t plane, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  float s = 0.f;
+  for (int z = 0; z < nplanes; ++z) s += part[(size_t)z * plane + i];
+  out[i] = s;
+}
+// r_i = sum over partial arrays (deterministic order)
+__global__ void k_rowdot_finalize(const float* __restrict__ rpart, int nparts, int n_rows, float* __restrict__ r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += rpart[(size_t)p * n_rows + i];
+  r[i] = s;
+}
+
+}  // namespace tgb

@@ -1,0 +1,810 @@
+// C-ABI of the B200-native map_cells_to_space hot path (see include/tangram_b200.h).
+// Host orchestration only; every kernel is hand-written for sm_100a in the .cuh files.
+#include "../../include/tangram_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_elem.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+using namespace tgb;
+
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(TGB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+#define CKS(expr)                 \
+  do {                            \
+    int s__ = (expr);             \
+    if (s__ != TGB200_OK) return s__; \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count, bool zero = true) {
+    release();
+    if (count == 0) return TGB200_OK;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; return fail(TGB200_ERR_CUDA, "cudaMalloc(%zu B): %s", count * sizeof(T), cudaGetErrorString(e)); }
+    n = count;
+    if (zero) {
+      e = cudaMemset(p, 0, count * sizeof(T));
+      if (e != cudaSuccess) return fail(TGB200_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    }
+    return TGB200_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+struct CsrDev {
+  DevBuf<int> indptr, indices;
+  DevBuf<float> vals;
+  bool set = false;
+  Csr view() const { return Csr{indptr.p, indices.p, vals.p}; }
+};
+
+struct KernelTimer;  // fwd
+
+struct tgb200_mapper {
+  tgb200_config cfg;
+  int N, V, K, T, Ke, ld;       // ld: leading dim of N x V arrays (elements)
+  int ct_off;
+  bool bf16;
+  // state
+  DevBuf<float> M, m, v;        // N x ld
+  int64_t step = 0;
+  // operands
+  DevBuf<float> Pf;             // N x ld  (fp32 mode)
+  DevBuf<__nv_bfloat16> Pb;     // N x ld  (bf16 mode)
+  DevBuf<float> Sx;             // N x Ke  S_ext = [S | density cols | ct_encode | 0]
+  DevBuf<__nv_bfloat16> Sxb;
+  DevBuf<float> G;              // V x Ke
+  DevBuf<float> d, dsrc;
+  DevBuf<RowStat> stats;
+  DevBuf<float> rowaux, rdot, rpart;
+  int r_parts = 0;
+  // forward / loss
+  int fwd_splits = 1;
+  DevBuf<float> Ypart;          // splits x V x Ke (only when splits > 1)
+  DevBuf<float> Y;              // V x Ke + 4 (exchange buffer)
+  DevBuf<float> dY;             // V x Ke
+  DevBuf<__nv_bfloat16> dYb;
+  DevBuf<float> ngc, ngr, WG, nwg, AG, nag, sgnG, Z, Zg, H;
+  DevBuf<float> colpart, colpart_nb, colpart_go, rowpart, ctpart;
+  DevBuf<float> coefA, coefB, coefAn, coefBn, coefAg, coefBg, coefAr, coefBr, densg;
+  CsrDev W, WT, F, FT, A, AT;
+  int nchunk = 0, ncolchunk = 0, n_ct_blocks = 0;
+  // history
+  DevBuf<float> hist;
+  int64_t hist_len = 0, hist_cap = 0;
+  // flags
+  bool have_expr = false, have_density = false, have_ct = false, have_mapping = false;
+  bool in_step = false;
+  int64_t launches = 0;
+  KernelTimer* timer = nullptr;
+  TcContext tc;                 // tensor maps etc. for the tcgen05 path
+};
+
+// Optional per-kernel CUDA-event timing (tgb200_profile_step).
+struct KernelTimer {
+  std::vector<const char*> names;
+  std::vector<cudaEvent_t> ev;
+};
+static void mark(tgb200_mapper* h, cudaStream_t s, const char* name) {
+  h->launches++;
+  if (h->timer) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    h->timer->names.push_back(name);
+    h->timer->ev.push_back(e);
+  }
+}
+#define LAUNCH_CHECK(name)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess) return fail(TGB200_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+    mark(h, s, name);                                                                       \
+  } while (0)
+
+static bool needs_rowaux(const tgb200_config& c) { return c.lambda_l1 != 0.f || c.lambda_l2 != 0.f; }
+static bool needs_rowscalars(const tgb200_config& c) {
+  return c.lambda_r != 0.f || c.lambda_l1 != 0.f || c.lambda_l2 != 0.f;
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" const char* tgb200_last_error(void) { return g_err; }
+extern "C" const char* tgb200_version(void) { return "tangram_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
+  if (!cfg || !out) return fail(TGB200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(tgb200_config))
+    return fail(TGB200_ERR_INVALID, "tgb200_config.struct_size=%d, expected %zu", cfg->struct_size, sizeof(tgb200_config));
+  if (cfg->n_cells <= 0 || cfg->n_voxels <= 0 || cfg->n_genes <= 0 || cfg->n_types < 0)
+    return fail(TGB200_ERR_INVALID, "bad shape cells=%d voxels=%d genes=%d types=%d", cfg->n_cells, cfg->n_voxels, cfg->n_genes, cfg->n_types);
+  if (cfg->lambda_g1 == 0.f) return fail(TGB200_ERR_INVALID, "lambda_g1 cannot be 0.");  // mapping_utils.py:206-207
+  if (cfg->precision != TGB200_PREC_FP32 && cfg->precision != TGB200_PREC_BF16)
+    return fail(TGB200_ERR_INVALID, "unknown precision %d", cfg->precision);
+  if (cfg->density_mode < 0 || cfg->density_mode > 2) return fail(TGB200_ERR_INVALID, "unknown density_mode %d", cfg->density_mode);
+  if (cfg->lambda_ct_islands > 0.f && cfg->n_types <= 0) return fail(TGB200_ERR_INVALID, "lambda_ct_islands > 0 needs n_types > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TGB200_ERR_NO_DEVICE, "no CUDA device visible: tangram_b200 has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(TGB200_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(TGB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  CK(cudaSetDevice(cfg->device));
+
+  tgb200_mapper* h = new tgb200_mapper();
+  h->cfg = *cfg;
+  if (h->cfg.n_cells_global <= 0) h->cfg.n_cells_global = cfg->n_cells;
+  if (h->cfg.adam_beta1 == 0.f) h->cfg.adam_beta1 = 0.9f;
+  if (h->cfg.adam_beta2 == 0.f) h->cfg.adam_beta2 = 0.999f;
+  if (h->cfg.adam_eps == 0.f) h->cfg.adam_eps = 1e-8f;
+  h->N = cfg->n_cells; h->V = cfg->n_voxels; h->K = cfg->n_genes; h->T = cfg->n_types;
+  h->bf16 = cfg->precision == TGB200_PREC_BF16;
+  h->ct_off = h->K + 2;
+  h->Ke = (int)round_up(h->K + 2 + h->T, 64);
+  h->ld = (int)round_up(h->V, 64);
+  const size_t nv = (size_t)h->N * h->ld, vk = (size_t)h->V * h->Ke;
+  int st = TGB200_OK;
+  auto A = [&](int s) { if (st == TGB200_OK) st = s; };
+  A(h->M.alloc(nv)); A(h->m.alloc(nv)); A(h->v.alloc(nv));
+  if (h->bf16) { A(h->Pb.alloc(nv)); A(h->Sxb.alloc((size_t)h->N * h->Ke)); A(h->dYb.alloc(vk)); }
+  else A(h->Pf.alloc(nv));
+  A(h->Sx.alloc((size_t)h->N * h->Ke));
+  A(h->G.alloc(vk));
+  A(h->d.alloc(h->V)); A(h->dsrc.alloc(h->N));
+  A(h->stats.alloc(h->N)); A(h->rowaux.alloc((size_t)2 * h->N)); A(h->rdot.alloc(h->N));
+  // forward split over cells so that the grid covers the 148 SMs (deterministic partial planes)
+  {
+    const int tiles = (int)(ceil_div(h->V, 128) * ceil_div(h->Ke, 128));
+    int s = (int)ceil_div(2 * 148, tiles);
+    const int max_s = (int)ceil_div(h->N, 512);
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    if (h->bf16) s = tc_forward_splits(h->N, h->V, h->Ke);
+    h->fwd_splits = s;
+    if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
+  }
+  A(h->Y.alloc(vk + 4)); A(h->dY.alloc(vk));
+  h->r_parts = (int)ceil_div(h->Ke, h->bf16 ? TC_RDOT_BN : SG_BN) * (h->bf16 ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1);
+  A(h->rpart.alloc((size_t)h->r_parts * h->N));
+  A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
+  h->nchunk = (int)ceil_div(h->V, kLossRows);
+  h->ncolchunk = (int)ceil_div(h->Ke, kLossCols);
+  A(h->colpart.alloc((size_t)h->nchunk * 3 * h->Ke));
+  A(h->coefA.alloc(h->Ke)); A(h->coefB.alloc(h->Ke));
+  A(h->densg.alloc(h->V));
+  if (cfg->lambda_g2 != 0.f) { A(h->rowpart.alloc((size_t)h->ncolchunk * h->V * 2)); A(h->coefAr.alloc(h->V)); A(h->coefBr.alloc(h->V)); }
+  if (cfg->lambda_neighborhood_g1 > 0.f) {
+    A(h->WG.alloc(vk)); A(h->nwg.alloc(h->Ke)); A(h->Z.alloc(vk)); A(h->colpart_nb.alloc((size_t)h->nchunk * 2 * h->Ke));
+    A(h->coefAn.alloc(h->Ke)); A(h->coefBn.alloc(h->Ke));
+  }
+  if (cfg->lambda_getis_ord > 0.f) {
+    A(h->AG.alloc(vk)); A(h->nag.alloc(h->Ke)); A(h->sgnG.alloc(h->Ke)); A(h->Zg.alloc(vk));
+    A(h->colpart_go.alloc((size_t)h->nchunk * 2 * h->Ke)); A(h->coefAg.alloc(h->Ke)); A(h->coefBg.alloc(h->Ke));
+  }
+  if (cfg->lambda_ct_islands > 0.f) {
+    h->n_ct_blocks = (int)ceil_div((int64_t)h->V * h->T, 256);
+    A(h->H.alloc((size_t)h->V * h->T)); A(h->ctpart.alloc(h->n_ct_blocks));
+  }
+  if (st == TGB200_OK && h->bf16) st = tc_init(h->tc, g_err, sizeof(g_err));
+  if (st != TGB200_OK) { delete h; return st; }
+  CK(cudaDeviceSynchronize());
+  *out = h;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_destroy(tgb200_mapper* h) {
+  if (!h) return TGB200_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  delete h;
+  return TGB200_OK;
+}
+
+// copy a dense host-or-device row-major matrix into a padded device matrix at a column offset
+static int upload_padded(tgb200_mapper* h, const float* src, int rows, int cols, float* dst, int ld, int col_off,
+                         cudaStream_t s) {
+  DevBuf<float> tmp;
+  CKS(tmp.alloc((size_t)rows * cols, false));
+  CK(cudaMemcpyAsync(tmp.p, src, (size_t)rows * cols * sizeof(float), cudaMemcpyDefault, s));
+  const long long n = (long long)rows * cols;
+  k_pack_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(tmp.p, rows, cols, dst, ld, col_off);
+  LAUNCH_CHECK("pack_rows");
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+static int refresh_bf16_operands(tgb200_mapper* h, cudaStream_t s) {
+  if (!h->bf16) return TGB200_OK;
+  const long long n = (long long)h->N * h->Ke;
+  k_f32_to_bf16<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(h->Sx.p, h->Sxb.p, n);
+  LAUNCH_CHECK("f32_to_bf16");
+  return TGB200_OK;
+}
+
+static int fill_density_cols(tgb200_mapper* h, cudaStream_t s) {
+  const float* w = (h->cfg.density_mode == TGB200_DENSITY_SOURCE) ? h->dsrc.p : nullptr;
+  k_fill_density_cols<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->Sx.p, h->N, h->Ke, h->K, w, h->bf16 ? 1 : 0);
+  LAUNCH_CHECK("fill_density_cols");
+  return refresh_bf16_operands(h, s);
+}
+
+static int precompute_graph_constants(tgb200_mapper* h, cudaStream_t s) {
+  if (!h->have_expr) return TGB200_OK;
+  dim3 grid((unsigned)ceil_div(h->Ke, 128), h->V);
+  if (h->cfg.lambda_neighborhood_g1 > 0.f && h->W.set) {
+    k_spmm<<<grid, 128, 0, s>>>(h->V, h->K, h->Ke, h->W.view(), h->G.p, h->WG.p);
+    LAUNCH_CHECK("spmm");
+    k_col_norms<<<(unsigned)ceil_div(h->K, 128), 128, 0, s>>>(h->V, h->K, h->Ke, h->WG.p, h->nwg.p, nullptr);
+    LAUNCH_CHECK("col_norms");
+  }
+  if (h->cfg.lambda_getis_ord > 0.f && h->A.set) {
+    k_spmm<<<grid, 128, 0, s>>>(h->V, h->K, h->Ke, h->A.view(), h->G.p, h->AG.p);
+    LAUNCH_CHECK("spmm");
+    k_col_norms<<<(unsigned)ceil_div(h->K, 128), 128, 0, s>>>(h->V, h->K, h->Ke, h->AG.p, h->nag.p, nullptr);
+    LAUNCH_CHECK("col_norms");
+    k_col_norms<<<(unsigned)ceil_div(h->K, 128), 128, 0, s>>>(h->V, h->K, h->Ke, h->G.p, h->ngc.p, h->sgnG.p);
+    LAUNCH_CHECK("col_norms");
+  }
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_expression(tgb200_mapper* h, const float* S, const float* G, void* stream) {
+  if (!h || !S || !G) return fail(TGB200_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->Sx.p, 0, h->Sx.n * sizeof(float), s));
+  CK(cudaMemsetAsync(h->G.p, 0, h->G.n * sizeof(float), s));
+  CKS(upload_padded(h, S, h->N, h->K, h->Sx.p, h->Ke, 0, s));
+  CKS(upload_padded(h, G, h->V, h->K, h->G.p, h->Ke, 0, s));
+  k_col_norms<<<(unsigned)ceil_div(h->K, 128), 128, 0, s>>>(h->V, h->K, h->Ke, h->G.p, h->ngc.p, nullptr);
+  LAUNCH_CHECK("col_norms");
+  k_row_norms<<<(unsigned)ceil_div(h->V, 8), 256, 0, s>>>(h->V, h->K, h->Ke, h->G.p, h->ngr.p);
+  LAUNCH_CHECK("row_norms");
+  h->have_expr = true;
+  h->have_ct = false;
+  CKS(fill_density_cols(h, s));
+  CKS(precompute_graph_constants(h, s));
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_density(tgb200_mapper* h, const float* d, const float* d_source, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->cfg.density_mode != TGB200_DENSITY_NONE && !d) return fail(TGB200_ERR_INVALID, "density_mode != NONE needs d");
+  if (h->cfg.density_mode == TGB200_DENSITY_SOURCE && !d_source) return fail(TGB200_ERR_INVALID, "DENSITY_SOURCE needs d_source");
+  if (d) CK(cudaMemcpyAsync(h->d.p, d, h->V * sizeof(float), cudaMemcpyDefault, s));
+  if (d_source) CK(cudaMemcpyAsync(h->dsrc.p, d_source, h->N * sizeof(float), cudaMemcpyDefault, s));
+  h->have_density = true;
+  if (h->have_expr) CKS(fill_density_cols(h, s));
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_ct_encode(tgb200_mapper* h, const float* E, void* stream) {
+  if (!h || !E) return fail(TGB200_ERR_INVALID, "null argument");
+  if (h->T <= 0) return fail(TGB200_ERR_INVALID, "handle was created with n_types == 0");
+  if (!h->have_expr) return fail(TGB200_ERR_STATE, "call tgb200_set_expression first");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CKS(upload_padded(h, E, h->N, h->T, h->Sx.p, h->Ke, h->ct_off, s));
+  CKS(refresh_bf16_operands(h, s));
+  h->have_ct = true;
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+static int upload_csr(CsrDev& dst, int V, const int32_t* indptr, const int32_t* indices, const float* vals, int64_t nnz) {
+  CKS(dst.indptr.alloc(V + 1, false));
+  CKS(dst.indices.alloc(nnz > 0 ? nnz : 1, false));
+  CKS(dst.vals.alloc(nnz > 0 ? nnz : 1, false));
+  CK(cudaMemcpy(dst.indptr.p, indptr, (V + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  if (nnz > 0) {
+    CK(cudaMemcpy(dst.indices.p, indices, nnz * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dst.vals.p, vals, nnz * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  dst.set = true;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indptr, const int32_t* indices,
+                                const float* values, int64_t nnz, void* stream) {
+  if (!h || !indptr || (nnz > 0 && (!indices || !values))) return fail(TGB200_ERR_INVALID, "null argument");
+  if (which < 0 || which > 2) return fail(TGB200_ERR_INVALID, "unknown graph id %d", which);
+  const int V = h->V;
+  if (indptr[0] != 0 || indptr[V] != nnz) return fail(TGB200_ERR_INVALID, "CSR indptr does not match nnz=%lld", (long long)nnz);
+  for (int64_t e = 0; e < nnz; ++e)
+    if (indices[e] < 0 || indices[e] >= V) return fail(TGB200_ERR_INVALID, "CSR column index %d out of range", indices[e]);
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  // transpose on the host (counting sort): backward needs Op^T
+  std::vector<int> tptr(V + 1, 0), tidx(nnz);
+  std::vector<float> tval(nnz);
+  for (int64_t e = 0; e < nnz; ++e) tptr[indices[e] + 1]++;
+  for (int j = 0; j < V; ++j) tptr[j + 1] += tptr[j];
+  {
+    std::vector<int> cur(tptr.begin(), tptr.end() - 1);
+    for (int j = 0; j < V; ++j)
+      for (int e = indptr[j]; e < indptr[j + 1]; ++e) {
+        const int q = cur[indices[e]]++;
+        tidx[q] = j; tval[q] = values[e];
+      }
+  }
+  CsrDev* fw = which == 0 ? &h->W : which == 1 ? &h->F : &h->A;
+  CsrDev* bw = which == 0 ? &h->WT : which == 1 ? &h->FT : &h->AT;
+  CKS(upload_csr(*fw, V, indptr, indices, values, nnz));
+  CKS(upload_csr(*bw, V, tptr.data(), tidx.data(), tval.data(), nnz));
+  CKS(precompute_graph_constants(h, s));
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+static int reset_optimizer(tgb200_mapper* h, cudaStream_t s) {
+  CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
+  CK(cudaMemsetAsync(h->v.p, 0, h->v.n * sizeof(float), s));
+  h->step = 0;
+  h->hist_len = 0;
+  h->in_step = false;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* stream) {
+  if (!h || !M0) return fail(TGB200_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->M.p, 0, h->M.n * sizeof(float), s));
+  CK(cudaMemcpy2DAsync(h->M.p, (size_t)h->ld * sizeof(float), M0, (size_t)h->V * sizeof(float),
+                       (size_t)h->V * sizeof(float), h->N, cudaMemcpyDefault, s));
+  CKS(reset_optimizer(h, s));
+  h->have_mapping = true;
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  const long long nq = (long long)h->N * (h->ld / 4);
+  k_init_normal<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->M.p, h->N, h->V, h->ld, seed);
+  LAUNCH_CHECK("init_normal");
+  CKS(reset_optimizer(h, s));
+  h->have_mapping = true;
+  return TGB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename PT>
+static int launch_softmax_rows(tgb200_mapper* h, cudaStream_t s, PT* P, int want_entropy, float* rowaux) {
+  const int nvec = h->ld / 4;
+  constexpr int TH = 256;
+#define SMX(ITEMS)                                                                                  \
+  k_softmax_rows<PT, TH, ITEMS><<<h->N, TH, 0, s>>>(h->M.p, h->ld, h->V, P, h->ld, h->stats.p, rowaux, want_entropy)
+  if (nvec <= TH * 1) SMX(1);
+  else if (nvec <= TH * 2) SMX(2);
+  else if (nvec <= TH * 4) SMX(4);
+  else if (nvec <= TH * 8) SMX(8);
+  else if (nvec <= TH * 12) SMX(12);
+  else SMX(0);
+#undef SMX
+  LAUNCH_CHECK("softmax_rows");
+  return TGB200_OK;
+}
+
+static LossParams make_loss_params(tgb200_mapper* h) {
+  LossParams p;
+  memset(&p, 0, sizeof(p));
+  const tgb200_config& c = h->cfg;
+  p.V = h->V; p.K = h->K; p.Ke = h->Ke; p.T = h->T; p.ct_off = h->ct_off; p.density_mode = c.density_mode;
+  p.n_cells_global = c.n_cells_global;
+  p.lam_g1 = c.lambda_g1; p.lam_d = c.lambda_d; p.lam_g2 = c.lambda_g2; p.lam_r = c.lambda_r;
+  p.lam_l1 = c.lambda_l1; p.lam_l2 = c.lambda_l2; p.lam_nb = c.lambda_neighborhood_g1;
+  p.lam_ct = c.lambda_ct_islands; p.lam_go = c.lambda_getis_ord;
+  p.G = h->G.p; p.d = h->d.p; p.Y = h->Y.p; p.ngc = h->ngc.p; p.ngr = h->ngr.p;
+  p.W = h->W.view(); p.WT = h->WT.view(); p.F = h->F.view(); p.FT = h->FT.view(); p.A = h->A.view(); p.AT = h->AT.view();
+  p.WG = h->WG.p; p.nwg = h->nwg.p; p.AG = h->AG.p; p.nag = h->nag.p; p.sgnG = h->sgnG.p;
+  p.Z = h->Z.p; p.Zg = h->Zg.p; p.H = h->H.p;
+  p.colpart = h->colpart.p; p.colpart_nb = h->colpart_nb.p; p.colpart_go = h->colpart_go.p;
+  p.rowpart = h->rowpart.p; p.ctpart = h->ctpart.p; p.n_ct_blocks = h->n_ct_blocks;
+  p.coefA = h->coefA.p; p.coefB = h->coefB.p; p.coefAn = h->coefAn.p; p.coefBn = h->coefBn.p;
+  p.coefAg = h->coefAg.p; p.coefBg = h->coefBg.p; p.coefAr = h->coefAr.p; p.coefBr = h->coefBr.p;
+  p.densg = h->densg.p;
+  return p;
+}
+
+static int check_ready(tgb200_mapper* h) {
+  const tgb200_config& c = h->cfg;
+  if (!h->have_expr) return fail(TGB200_ERR_STATE, "tgb200_set_expression has not been called");
+  if (!h->have_mapping) return fail(TGB200_ERR_STATE, "no mapping: call tgb200_set_mapping or tgb200_init_mapping_normal");
+  if (c.density_mode != TGB200_DENSITY_NONE && !h->have_density) return fail(TGB200_ERR_STATE, "density term enabled but tgb200_set_density not called");
+  if (c.lambda_ct_islands > 0.f && (!h->have_ct || !h->F.set)) return fail(TGB200_ERR_STATE, "lambda_ct_islands > 0 needs ct_encode and the neighborhood_filter graph");
+  if (c.lambda_neighborhood_g1 > 0.f && !h->W.set) return fail(TGB200_ERR_STATE, "lambda_neighborhood_g1 > 0 needs the voxel_weights graph");
+  if (c.lambda_getis_ord > 0.f && !h->A.set) return fail(TGB200_ERR_STATE, "lambda_getis_ord > 0 needs the spatial_weights graph");
+  return TGB200_OK;
+}
+
+// forward: P, row statistics, Y_ext partial sums over this handle's cells
+static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
+  float* rowaux = needs_rowaux(h->cfg) ? h->rowaux.p : nullptr;
+  if (h->bf16) CKS(launch_softmax_rows<__nv_bfloat16>(h, s, h->Pb.p, want_entropy, rowaux));
+  else CKS(launch_softmax_rows<float>(h, s, h->Pf.p, want_entropy, rowaux));
+  const size_t vk = (size_t)h->V * h->Ke;
+  float* out = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
+  if (h->bf16) {
+    CKS(tc_forward(h->tc, h->Pb.p, h->Sxb.p, out, h->N, h->V, h->Ke, h->ld, h->fwd_splits, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_fwd");
+  } else {
+    GemmArgs g;
+    g.A = h->Pf.p; g.lda = h->ld; g.B = h->Sx.p; g.ldb = h->Ke;
+    g.M = h->V; g.N = h->Ke; g.K = h->N;
+    g.k_per_split = (int)round_up(ceil_div(h->N, h->fwd_splits), 16);
+    EpiStorePartial epi{out, h->Ke, vk};
+    dim3 grid((unsigned)ceil_div(h->Ke, SG_BN), (unsigned)ceil_div(h->V, SG_BM), h->fwd_splits);
+    k_gemm_simt<false, false, EpiStorePartial><<<grid, SG_THREADS, 0, s>>>(g, epi);
+    LAUNCH_CHECK("simt_gemm_fwd");
+  }
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_step_begin(tgb200_mapper* h, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CKS(check_ready(h));
+  if (h->in_step) return fail(TGB200_ERR_STATE, "step_begin called twice without step_end");
+  CKS(forward_pass(h, s, h->cfg.lambda_r != 0.f ? 1 : 0));
+  const size_t vk = (size_t)h->V * h->Ke;
+  if (needs_rowscalars(h->cfg)) {
+    k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, needs_rowaux(h->cfg) ? h->rowaux.p : nullptr, h->N, h->Y.p + vk);
+    LAUNCH_CHECK("row_scalar_reduce");
+  }
+  if (h->cfg.n_cells_global != h->N && h->fwd_splits > 1) {
+    // sharded: the exchange buffer must hold this rank's complete partial sum
+    k_sum_planes<<<(unsigned)ceil_div(vk, 256), 256, 0, s>>>(h->Ypart.p, h->fwd_splits, vk, h->Y.p);
+    LAUNCH_CHECK("sum_planes");
+  }
+  h->in_step = true;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_exchange_buffer(tgb200_mapper* h, float** device_ptr, int64_t* n_floats) {
+  if (!h || !device_ptr || !n_floats) return fail(TGB200_ERR_INVALID, "null argument");
+  *device_ptr = h->Y.p;
+  *n_floats = (int64_t)h->V * h->Ke + 4;
+  return TGB200_OK;
+}
+
+static int ensure_history(tgb200_mapper* h, int64_t need, cudaStream_t s) {
+  if (need <= h->hist_cap) return TGB200_OK;
+  int64_t cap = h->hist_cap ? h->hist_cap : 1024;
+  while (cap < need) cap *= 2;
+  DevBuf<float> nb;
+  CKS(nb.alloc((size_t)cap * TGB200_HIST_COLS));
+  if (h->hist_len > 0) {
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpy(nb.p, h->hist.p, (size_t)h->hist_len * TGB200_HIST_COLS * sizeof(float), cudaMemcpyDeviceToDevice));
+  }
+  h->hist.release();
+  h->hist.p = nb.p; h->hist.n = nb.n; nb.p = nullptr; nb.n = 0;
+  h->hist_cap = cap;
+  return TGB200_OK;
+}
+
+// everything on V x Ke: reductions, scalars + history row, dY_ext
+static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool reduce_partials_first) {
+  LossParams p = make_loss_params(h);
+  const tgb200_config& c = h->cfg;
+  dim3 rgrid(h->ncolchunk, h->nchunk);
+  const float* part = (h->fwd_splits > 1 && reduce_partials_first) ? h->Ypart.p : h->Y.p;
+  const int nsplit = (h->fwd_splits > 1 && reduce_partials_first) ? h->fwd_splits : 1;
+  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, nsplit, c.lambda_g2 != 0.f ? 1 : 0);
+  LAUNCH_CHECK("loss_reduce");
+  if (c.lambda_neighborhood_g1 > 0.f) {
+    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->W.view(), h->Y.p, h->WG.p, h->Z.p, h->colpart_nb.p);
+    LAUNCH_CHECK("spatial_colstats");
+  }
+  if (c.lambda_getis_ord > 0.f) {
+    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->A.view(), h->Y.p, h->AG.p, h->Zg.p, h->colpart_go.p);
+    LAUNCH_CHECK("spatial_colstats");
+  }
+  if (c.lambda_ct_islands > 0.f) {
+    k_ct_islands<<<h->n_ct_blocks, 256, 0, s>>>(p);
+    LAUNCH_CHECK("ct_islands");
+  }
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, h->nchunk, h->ncolchunk, hist_row);
+  LAUNCH_CHECK("loss_scalars");
+  dim3 dgrid(h->ncolchunk, h->V);
+  k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->dY.p, h->bf16 ? h->dYb.p : nullptr);
+  LAUNCH_CHECK("dy_assemble");
+  return TGB200_OK;
+}
+
+static AdamScalars adam_scalars(const tgb200_config& c, int64_t t, float lr) {
+  // torch/optim/adam.py (_single_tensor_adam, non-capturable): python-double scalar math
+  const double b1 = (double)c.adam_beta1, b2 = (double)c.adam_beta2;
+  const double bc1 = 1.0 - std::pow(b1, (double)t), bc2 = 1.0 - std::pow(b2, (double)t);
+  AdamScalars a;
+  a.beta1 = c.adam_beta1; a.beta2 = c.adam_beta2;
+  a.one_minus_beta1 = (float)(1.0 - b1); a.one_minus_beta2 = (float)(1.0 - b2);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)std::sqrt(bc2);
+  a.eps = c.adam_eps;
+  return a;
+}
+
+extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->in_step) return fail(TGB200_ERR_STATE, "step_end without step_begin");
+  CKS(ensure_history(h, h->hist_len + 1, s));
+  float* hist_row = h->hist.p + (size_t)h->hist_len * TGB200_HIST_COLS;
+  // sharded: the caller all-reduced Y (already the sum of every rank's partial planes)
+  const bool sharded = h->cfg.n_cells_global != h->N;
+  CKS(loss_stage(h, s, hist_row, !sharded));
+
+  const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
+  if (h->bf16) {
+    CKS(tc_rowdot(h->tc, h->Pb.p, h->dYb.p, h->Sx.p, h->rpart.p, h->N, h->V, h->Ke, h->ld, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_rowdot");
+  } else {
+    GemmArgs g;
+    g.A = h->Pf.p; g.lda = h->ld; g.B = h->dY.p; g.ldb = h->Ke;
+    g.M = h->N; g.N = h->Ke; g.K = h->V; g.k_per_split = (int)round_up(h->V, 16);
+    EpiRowDot epi{h->Sx.p, h->Ke, h->rpart.p};
+    dim3 grid((unsigned)ceil_div(h->Ke, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
+    k_gemm_simt<true, false, EpiRowDot><<<grid, SG_THREADS, 0, s>>>(g, epi);
+    LAUNCH_CHECK("simt_gemm_rowdot");
+  }
+  k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p);
+  LAUNCH_CHECK("rowdot_finalize");
+  if (h->bf16) {
+    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, h->stats.p, h->rdot.p, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+    CKS(tc_backward(h->tc, h->Sxb.p, h->dYb.p, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_bwd_adam");
+  } else {
+    GemmArgs g;
+    g.A = h->Sx.p; g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
+    g.M = h->N; g.N = h->V; g.K = h->Ke; g.k_per_split = h->Ke;
+    EpiAdam epi{h->M.p, h->m.p, h->v.p, h->ld, h->V, h->stats.p, h->rdot.p, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+    dim3 grid((unsigned)ceil_div(h->V, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
+    k_gemm_simt<true, true, EpiAdam><<<grid, SG_THREADS, 0, s>>>(g, epi);
+    LAUNCH_CHECK("simt_gemm_bwd_adam");
+  }
+  h->step++;
+  h->hist_len++;
+  h->in_step = false;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_run(tgb200_mapper* h, int32_t n_steps, float lr, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (n_steps < 0) return fail(TGB200_ERR_INVALID, "n_steps < 0");
+  if (h->cfg.n_cells_global != h->N) return fail(TGB200_ERR_STATE, "cell-sharded handle: use step_begin / all-reduce / step_end");
+  CKS(ensure_history(h, h->hist_len + n_steps, (cudaStream_t)stream));
+  for (int i = 0; i < n_steps; ++i) {
+    CKS(tgb200_step_begin(h, stream));
+    CKS(tgb200_step_end(h, lr, stream));
+  }
+  return TGB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" int tgb200_history_len(tgb200_mapper* h, int64_t* n) {
+  if (!h || !n) return fail(TGB200_ERR_INVALID, "null argument");
+  *n = h->hist_len;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_get_history(tgb200_mapper* h, int64_t first, int64_t count, float* out, void* stream) {
+  if (!h || (!out && count > 0)) return fail(TGB200_ERR_INVALID, "null argument");
+  if (first < 0 || count < 0 || first + count > h->hist_len) return fail(TGB200_ERR_INVALID, "history range [%lld,%lld) outside [0,%lld)", (long long)first, (long long)(first + count), (long long)h->hist_len);
+  if (count == 0) return TGB200_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out, h->hist.p + (size_t)first * TGB200_HIST_COLS, (size_t)count * TGB200_HIST_COLS * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_get_mapping(tgb200_mapper* h, float* out, void* stream) {
+  if (!h || !out) return fail(TGB200_ERR_INVALID, "null argument");
+  if (!h->have_mapping) return fail(TGB200_ERR_STATE, "no mapping set");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  DevBuf<float> tmp;
+  float* P = h->Pf.p;
+  if (h->bf16) { CKS(tmp.alloc((size_t)h->N * h->ld, false)); P = tmp.p; }
+  CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));      // :406-407
+  CK(cudaMemcpy2DAsync(out, (size_t)h->V * sizeof(float), P, (size_t)h->ld * sizeof(float),
+                       (size_t)h->V * sizeof(float), h->N, cudaMemcpyDefault, s));
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_get_state(tgb200_mapper* h, float* M, float* m, float* v, int64_t* step, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
+  if (M) CK(cudaMemcpy2DAsync(M, w, h->M.p, pitch, w, h->N, cudaMemcpyDefault, s));
+  if (m) CK(cudaMemcpy2DAsync(m, w, h->m.p, pitch, w, h->N, cudaMemcpyDefault, s));
+  if (v) CK(cudaMemcpy2DAsync(v, w, h->v.p, pitch, w, h->N, cudaMemcpyDefault, s));
+  if (step) *step = h->step;
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_state(tgb200_mapper* h, const float* M, const float* m, const float* v, int64_t step, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (step < 0) return fail(TGB200_ERR_INVALID, "step < 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
+  if (M) { CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; }
+  if (m) CK(cudaMemcpy2DAsync(h->m.p, pitch, m, w, w, h->N, cudaMemcpyDefault, s));
+  if (v) CK(cudaMemcpy2DAsync(h->v.p, pitch, v, w, w, h->N, cudaMemcpyDefault, s));
+  h->step = step;
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_project(tgb200_mapper* h, const float* X, int64_t n_cols, float* out, void* stream) {
+  if (!h || !X || !out || n_cols <= 0) return fail(TGB200_ERR_INVALID, "bad argument");
+  if (!h->have_mapping) return fail(TGB200_ERR_STATE, "no mapping set");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  // softmax(M)^T X in fp32, gene columns streamed through in chunks (tangram/utils.py:368)
+  DevBuf<float> Pt;
+  float* P = h->Pf.p;
+  if (h->bf16) { CKS(Pt.alloc((size_t)h->N * h->ld, false)); P = Pt.p; }
+  CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));
+  const int chunk = 2048;
+  const int ldc = (int)round_up(n_cols < chunk ? n_cols : chunk, 4);
+  DevBuf<float> Xc, Oc;
+  CKS(Xc.alloc((size_t)h->N * ldc)); CKS(Oc.alloc((size_t)h->V * ldc));
+  for (int64_t c0 = 0; c0 < n_cols; c0 += chunk) {
+    const int nc = (int)((n_cols - c0) < chunk ? (n_cols - c0) : chunk);
+    CK(cudaMemsetAsync(Xc.p, 0, Xc.n * sizeof(float), s));
+    CK(cudaMemcpy2DAsync(Xc.p, (size_t)ldc * sizeof(float), X + c0, (size_t)n_cols * sizeof(float),
+                         (size_t)nc * sizeof(float), h->N, cudaMemcpyDefault, s));
+    GemmArgs g;
+    g.A = P; g.lda = h->ld; g.B = Xc.p; g.ldb = ldc; g.M = h->V; g.N = nc; g.K = h->N;
+    g.k_per_split = (int)round_up(h->N, 16);
+    EpiStorePartial epi{Oc.p, ldc, 0};
+    dim3 grid((unsigned)ceil_div(nc, SG_BN), (unsigned)ceil_div(h->V, SG_BM), 1);
+    k_gemm_simt<false, false, EpiStorePartial><<<grid, SG_THREADS, 0, s>>>(g, epi);
+    LAUNCH_CHECK("simt_gemm_project");
+    CK(cudaMemcpy2DAsync(out + c0, (size_t)n_cols * sizeof(float), Oc.p, (size_t)ldc * sizeof(float),
+                         (size_t)nc * sizeof(float), h->V, cudaMemcpyDefault, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stream) {
+  if (!h || !out4) return fail(TGB200_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CKS(check_ready(h));
+  if (h->in_step) return fail(TGB200_ERR_STATE, "validation_terms inside a step");
+  if (h->cfg.n_cells_global != h->N) return fail(TGB200_ERR_UNSUPPORTED, "validation_terms on a sharded handle");
+  // _val_loss_fn (:311-356): a second forward on the train matrices
+  CKS(forward_pass(h, s, 1));
+  LossParams p = make_loss_params(h);
+  DevBuf<float> rowpart, coefAr, coefBr, hist, gnz;
+  CKS(rowpart.alloc((size_t)h->ncolchunk * h->V * 2)); CKS(coefAr.alloc(h->V)); CKS(coefBr.alloc(h->V));
+  CKS(hist.alloc(TGB200_HIST_COLS));
+  p.rowpart = rowpart.p; p.coefAr = coefAr.p; p.coefBr = coefBr.p;
+  p.lam_g2 = 1.f; p.lam_g1 = 1.f; p.lam_nb = 0.f; p.lam_go = 0.f; p.lam_ct = 0.f; p.density_mode = 0;
+  dim3 rgrid(h->ncolchunk, h->nchunk);
+  const float* part = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
+  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, h->fwd_splits, 1);
+  LAUNCH_CHECK("loss_reduce");
+  k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, nullptr, h->N, h->Y.p + (size_t)h->V * h->Ke);
+  LAUNCH_CHECK("row_scalar_reduce");
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, h->nchunk, h->ncolchunk, hist.p);
+  LAUNCH_CHECK("loss_scalars");
+  // sparsity-weighted gene score needs per-gene cosines: recover them from coefA/coefB on the host
+  std::vector<float> hrow(TGB200_HIST_COLS), cA(h->K), cB(h->K), Gh((size_t)h->V * h->Ke), tail(4);
+  CK(cudaMemcpyAsync(hrow.data(), hist.p, sizeof(float) * TGB200_HIST_COLS, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cA.data(), h->coefA.p, sizeof(float) * h->K, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cB.data(), h->coefB.p, sizeof(float) * h->K, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(Gh.data(), h->G.p, sizeof(float) * Gh.size(), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(tail.data(), h->Y.p + (size_t)h->V * h->Ke, sizeof(float) * 4, cudaMemcpyDeviceToHost, s));
+  std::vector<float> ngc(h->K);
+  CK(cudaMemcpyAsync(ngc.data(), h->ngc.p, sizeof(float) * h->K, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  // cos_k = coefB_k * K * ny^2 with ny = 1/(coefA_k * K * ng)  (lam_g1 = 1 here)
+  double wsum = 0.0, acc = 0.0;
+  for (int k = 0; k < h->K; ++k) {
+    long nz = 0;
+    for (int j = 0; j < h->V; ++j) nz += Gh[(size_t)j * h->Ke + k] != 0.f;
+    const double w = (double)nz / h->V;       // 1 - gene_sparsity (:330)
+    const double ny = 1.0 / ((double)cA[k] * h->K * ngc[k]);
+    const double cosk = (double)cB[k] * h->K * ny * ny;
+    wsum += w; acc += cosk * w;
+  }
+  const float gv = hrow[1], vg = hrow[2];
+  out4[0] = gv + vg;                                   // expression_sim (:328)
+  out4[1] = gv;                                        // gv_sim (:326)
+  out4[2] = (float)(acc / wsum);                       // sp_sparsity_weighted_gv_sim (:331)
+  out4[3] = -(tail[0] / logf((float)h->V)) / h->N;     // entropy (:333)
+  return TGB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" int tgb200_kernel_launches(tgb200_mapper* h, int64_t* n) {
+  if (!h || !n) return fail(TGB200_ERR_INVALID, "null argument");
+  *n = h->launches;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_profile_step(tgb200_mapper* h, float lr, void* stream, const char** names, float* ms,
+                                   int32_t cap, int32_t* n) {
+  if (!h || !names || !ms || !n) return fail(TGB200_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  KernelTimer t;
+  cudaEvent_t e0;
+  CK(cudaEventCreate(&e0));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(e0, s));
+  h->timer = &t;
+  int st = tgb200_step_begin(h, stream);
+  if (st == TGB200_OK) st = tgb200_step_end(h, lr, stream);
+  h->timer = nullptr;
+  cudaStreamSynchronize(s);
+  int cnt = 0;
+  cudaEvent_t prev = e0;
+  for (size_t i = 0; i < t.ev.size(); ++i) {
+    float f = 0.f;
+    cudaEventElapsedTime(&f, prev, t.ev[i]);
+    if (cnt < cap) { names[cnt] = t.names[i]; ms[cnt] = f; cnt++; }
+    prev = t.ev[i];
+  }
+  cudaEventDestroy(e0);
+  for (auto e : t.ev) cudaEventDestroy(e);
+  *n = cnt;
+  return st;
+}
+
+extern "C" int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  const double N = h->N, V = h->V, K = h->K, T = h->T;
+  const double sS = h->bf16 ? 2.0 : 4.0;
+  if (hbm_bytes) *hbm_bytes = 28.0 * N * V + 2.0 * sS * N * K + 8.0 * V * K;
+  if (flops) *flops = 4.0 * N * V * K + (h->cfg.lambda_ct_islands > 0.f ? 4.0 * N * V * T : 0.0);
+  return TGB200_OK;
+}

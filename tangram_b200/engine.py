@@ -1,0 +1,119 @@
+"""Thin object wrapper over the C-ABI handle (include/tangram_b200.h) for callers that
+manage their own buffers (bench.py, multi-GPU drivers).  `Mapper` is the reference-shaped
+front end; this is the explicit one."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class Engine:
+    def __init__(self, n_cells, n_voxels, n_genes, *, n_types=0, n_cells_global=None, device=0,
+                 precision="fp32", density_mode=_lib.DENSITY_CELLS, **lambdas):
+        self._lib = _lib.load()
+        cfg = _lib.Config()
+        cfg.struct_size = ctypes.sizeof(_lib.Config)
+        cfg.device = device
+        cfg.n_cells, cfg.n_voxels, cfg.n_genes, cfg.n_types = n_cells, n_voxels, n_genes, n_types
+        cfg.n_cells_global = n_cells_global or n_cells
+        cfg.precision = _lib.PREC[precision]
+        cfg.density_mode = density_mode
+        cfg.lambda_g1 = lambdas.pop("lambda_g1", 1.0)
+        cfg.lambda_d = lambdas.pop("lambda_d", 1.0 if density_mode != _lib.DENSITY_NONE else 0.0)
+        for k in ("lambda_g2", "lambda_r", "lambda_l1", "lambda_l2", "lambda_neighborhood_g1",
+                  "lambda_ct_islands", "lambda_getis_ord"):
+            setattr(cfg, k, lambdas.pop(k, 0.0))
+        if lambdas:
+            raise TypeError(f"unknown arguments {sorted(lambdas)}")
+        cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps = 0.9, 0.999, 1e-8
+        self.cfg = cfg
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.tgb200_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.tgb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @staticmethod
+    def _s(stream):
+        return ctypes.c_void_p(stream) if stream else None
+
+    def set_expression(self, S, G, stream=None):
+        _lib.check(self._lib.tgb200_set_expression(self._h, _lib.ptr(S), _lib.ptr(G), self._s(stream)))
+
+    def set_density(self, d, d_source=None, stream=None):
+        _lib.check(self._lib.tgb200_set_density(self._h, _lib.ptr(d), _lib.ptr(d_source), self._s(stream)))
+
+    def set_ct_encode(self, E, stream=None):
+        _lib.check(self._lib.tgb200_set_ct_encode(self._h, _lib.ptr(E), self._s(stream)))
+
+    def set_graph(self, which, csr, stream=None):
+        csr = csr.tocsr()
+        csr.sort_indices()
+        ip = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        vv = np.ascontiguousarray(csr.data, dtype=np.float32)
+        _lib.check(self._lib.tgb200_set_graph(self._h, which, _lib.ptr(ip), _lib.ptr(ix), _lib.ptr(vv), len(vv),
+                                              self._s(stream)))
+
+    def set_mapping(self, M0, stream=None):
+        _lib.check(self._lib.tgb200_set_mapping(self._h, _lib.ptr(M0), self._s(stream)))
+
+    def init_mapping_normal(self, seed, stream=None):
+        _lib.check(self._lib.tgb200_init_mapping_normal(self._h, seed, self._s(stream)))
+
+    def run(self, n_steps, lr=0.1, stream=None):
+        _lib.check(self._lib.tgb200_run(self._h, n_steps, lr, self._s(stream)))
+
+    def step_begin(self, stream=None):
+        _lib.check(self._lib.tgb200_step_begin(self._h, self._s(stream)))
+
+    def step_end(self, lr=0.1, stream=None):
+        _lib.check(self._lib.tgb200_step_end(self._h, lr, self._s(stream)))
+
+    def exchange_tensor(self):
+        import torch
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self._lib.tgb200_exchange_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (p.value, False),
+                                        "version": 3, "strides": None}
+        return torch.as_tensor(_Wrap(), device=f"cuda:{self.cfg.device}")
+
+    def history(self):
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(n)))
+        out = np.empty((n.value, _lib.HIST_COLS), dtype=np.float32)
+        if n.value:
+            _lib.check(self._lib.tgb200_get_history(self._h, 0, n.value, _lib.ptr(out), None))
+        return out
+
+    def get_mapping(self, out, stream=None):
+        _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(out), self._s(stream)))
+        return out
+
+    def kernel_launches(self):
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+    def profile_step(self, lr=0.1, stream=None, cap=64):
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = ctypes.c_int32()
+        _lib.check(self._lib.tgb200_profile_step(self._h, lr, self._s(stream), names, ms, cap, ctypes.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def algorithmic_cost(self):
+        b, f = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self._lib.tgb200_algorithmic_cost(self._h, ctypes.byref(b), ctypes.byref(f)))
+        return b.value, f.value

@@ -1,0 +1,316 @@
+"""
+Drop-in replacement for the reference optimizer class `Mapper`
+(/root/reference/tangram/mapping_optimizer.py:14-408), running on the sm_100a C-ABI
+library (include/tangram_b200.h).  Same constructor keywords, same `train()` signature,
+same return types and history conventions.  There is no CPU path: `device` must be a
+CUDA device with compute capability 10.x.
+
+Additions (keyword-only, all optional):
+  precision   "fp32" (parity mode, default) | "bf16" (tcgen05 tensor cores)
+  M0          explicit initial mapping (ndarray N x V); default is the reference draw
+  process_group / shard  cell-sharded multi-GPU operation (one process per GPU): every rank passes the
+              full S / M0 and keeps rows shard_rows(N, rank, world)
+  n_cells_global         pre-sharded variant: S, M0, d_source, ct_encode already hold only this rank's rows
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_HIST_KEYS = ["total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg"]
+_VAL_KEYS = ["val_total_loss", "val_gene_sim", "val_sp_sparsity_weighted_sim", "val_entropy"]
+# (history column, printed name) in the reference's print order (mapping_optimizer.py:273-298)
+_PRINT_TERMS = [
+    (1, "Gene-voxel score"), (2, "Voxel-gene score"), (3, "Cell densities reg"), (4, "Entropy reg"),
+    (5, "L1 reg"), (6, "L2 reg"), (7, "Spatial weighted score"), (8, "Cell type islands penalty"),
+    (9, "Getis-Ord score"),
+]
+
+
+def _device_index(device):
+    """'cuda', 'cuda:1', torch.device -> ordinal.  'cpu' is refused: no CPU fallback."""
+    s = str(device)
+    if s.startswith("cuda"):
+        return int(s.split(":")[1]) if ":" in s else 0
+    raise ValueError(
+        f"tangram_b200.Mapper runs on B200 GPUs only (device={device!r}); "
+        "use the reference implementation for device='cpu'")
+
+
+def _to_csr(mat, n):
+    """dense ndarray (what the reference passes, mapping_utils.py:319-329) or scipy sparse -> CSR triplet."""
+    import scipy.sparse as sp
+    if mat is None:
+        return None
+    if hasattr(mat, "detach"):
+        mat = mat.detach().cpu().numpy()
+    csr = mat.tocsr() if sp.issparse(mat) else sp.csr_matrix(np.asarray(mat))
+    if csr.shape != (n, n):
+        raise ValueError(f"spatial operator has shape {csr.shape}, expected {(n, n)}")
+    csr.sort_indices()
+    return (np.ascontiguousarray(csr.indptr, dtype=np.int32),
+            np.ascontiguousarray(csr.indices, dtype=np.int32),
+            np.ascontiguousarray(csr.data, dtype=np.float32))
+
+
+def format_terms(row):
+    """The reference's print line (mapping_optimizer.py:300-307) from one history row."""
+    msg = ["{}: {:.3f}".format(name, row[c]) for c, name in _PRINT_TERMS if not np.isnan(row[c])]
+    return str(msg).replace("[", "").replace("]", "").replace("'", "")
+
+
+class Mapper:
+    def __init__(
+        self,
+        S,
+        G,
+        train_genes_idx=None,
+        val_genes_idx=None,
+        d=None,
+        d_source=None,
+        lambda_g1=1.0,
+        lambda_d=0,
+        lambda_g2=0,
+        lambda_r=0,
+        lambda_l1=0,
+        lambda_l2=0,
+        lambda_neighborhood_g1=0,
+        voxel_weights=None,
+        lambda_getis_ord=0,
+        lambda_geary=0,
+        lambda_moran=0,
+        neighborhood_filter=None,
+        ct_encode=None,
+        lambda_ct_islands=0,
+        spatial_weights=None,
+        device="cuda:0",
+        adata_map=None,
+        random_state=None,
+        *,
+        precision="fp32",
+        M0=None,
+        process_group=None,
+        shard=None,
+        n_cells_global=None,
+    ):
+        if lambda_geary > 0 or lambda_moran > 0:
+            # mapping_optimizer.py:173-185: not on the accelerated path (Geary builds V x V x K)
+            raise NotImplementedError("lambda_moran / lambda_geary are not supported by tangram_b200")
+        if adata_map is not None:
+            raise NotImplementedError  # the reference raises here too (:151-153)
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {list(_lib.PREC)}")
+        self.device = device
+        self.random_state = random_state
+        self.precision = precision
+        self._lib = _lib.load()
+        self._h = None
+        self._pg = process_group
+
+        S = np.asarray(S, dtype=np.float32)
+        G = np.asarray(G, dtype=np.float32)
+        if train_genes_idx is not None:      # :87-92 (val subset is never read, :321-322)
+            S = S[:, train_genes_idx]
+            G = G[:, train_genes_idx]
+        S = np.ascontiguousarray(S)
+        G = np.ascontiguousarray(G)
+        if S.shape[1] != G.shape[1]:
+            raise ValueError("S and G must have the same number of genes")
+        n_rows_given, n_voxels, n_genes = S.shape[0], G.shape[0], S.shape[1]
+        presharded = n_cells_global is not None
+        n_cells_global = int(n_cells_global) if presharded else n_rows_given
+
+        self.target_density_enabled = d is not None
+        self.source_density_enabled = d_source is not None
+        density_mode = _lib.DENSITY_NONE
+        if self.target_density_enabled:
+            density_mode = _lib.DENSITY_SOURCE if self.source_density_enabled else _lib.DENSITY_CELLS
+        if ct_encode is not None:
+            ct_encode = np.ascontiguousarray(np.asarray(ct_encode, dtype=np.float32))
+        n_types = ct_encode.shape[1] if (ct_encode is not None and lambda_ct_islands > 0) else 0
+
+        # initial mapping: legacy numpy RNG, float64 draw, f32 cast; seeded only if truthy (:147-157)
+        if M0 is None:
+            if self.random_state:
+                np.random.seed(seed=self.random_state)
+            M0 = np.random.normal(0, 1, (n_rows_given, n_voxels))
+        M0 = np.asarray(M0)
+        if M0.shape != (n_rows_given, n_voxels):
+            raise ValueError("M0 has the wrong shape")
+
+        # cell-sharded operation: this rank keeps rows [r0, r1)
+        self._rows = (0, n_rows_given)
+        if presharded:
+            pass
+        elif shard is not None:
+            self._rows = (int(shard[0]), int(shard[1]))
+        elif process_group is not None:
+            import torch.distributed as dist
+            r, w = dist.get_rank(process_group), dist.get_world_size(process_group)
+            self._rows = shard_rows(n_cells_global, r, w)
+        r0, r1 = self._rows
+        sharded = (r1 - r0) != n_cells_global
+
+        cfg = _lib.Config()
+        cfg.struct_size = ctypes.sizeof(_lib.Config)
+        cfg.device = _device_index(device)
+        cfg.n_cells, cfg.n_voxels, cfg.n_genes, cfg.n_types = r1 - r0, n_voxels, n_genes, n_types
+        cfg.n_cells_global = n_cells_global
+        cfg.precision = _lib.PREC[precision]
+        cfg.density_mode = density_mode
+        cfg.lambda_g1, cfg.lambda_d, cfg.lambda_g2 = lambda_g1, lambda_d, lambda_g2
+        cfg.lambda_r, cfg.lambda_l1, cfg.lambda_l2 = lambda_r, lambda_l1, lambda_l2
+        cfg.lambda_neighborhood_g1 = lambda_neighborhood_g1
+        cfg.lambda_ct_islands = lambda_ct_islands
+        cfg.lambda_getis_ord = lambda_getis_ord
+        cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps = 0.9, 0.999, 1e-8   # torch.optim.Adam defaults (:373)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.tgb200_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self._cfg = cfg
+        self._sharded = sharded
+        self.n_cells, self.n_voxels, self.n_genes = r1 - r0, n_voxels, n_genes
+
+        L = self._lib
+        _lib.check(L.tgb200_set_expression(h, _lib.ptr(np.ascontiguousarray(S[r0:r1])), _lib.ptr(G), None))
+        if self.target_density_enabled:
+            dd = np.ascontiguousarray(np.asarray(d, dtype=np.float32))
+            ds = None
+            if self.source_density_enabled:
+                ds = np.ascontiguousarray(np.asarray(d_source, dtype=np.float32)[r0:r1])
+            _lib.check(L.tgb200_set_density(h, _lib.ptr(dd), _lib.ptr(ds), None))
+        graphs = []
+        if lambda_neighborhood_g1 > 0:
+            graphs.append((_lib.GRAPH_VOXEL_WEIGHTS, voxel_weights, "voxel_weights"))
+        if lambda_ct_islands > 0:
+            graphs.append((_lib.GRAPH_NEIGHBORHOOD_FILTER, neighborhood_filter, "neighborhood_filter"))
+        if lambda_getis_ord > 0:
+            graphs.append((_lib.GRAPH_SPATIAL_WEIGHTS, spatial_weights, "spatial_weights"))
+        for which, mat, name in graphs:
+            if mat is None:
+                raise ValueError(f"{name} is required by the enabled lambda")
+            indptr, indices, vals = _to_csr(mat, n_voxels)
+            _lib.check(L.tgb200_set_graph(h, which, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(vals),
+                                          len(vals), None))
+        if lambda_ct_islands > 0:
+            if ct_encode is None:
+                raise ValueError("ct_encode is required when lambda_ct_islands > 0")
+            _lib.check(L.tgb200_set_ct_encode(h, _lib.ptr(np.ascontiguousarray(ct_encode[r0:r1])), None))
+        M0 = np.ascontiguousarray(M0[r0:r1], dtype=np.float32)
+        _lib.check(L.tgb200_set_mapping(h, _lib.ptr(M0), None))
+
+    # ------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.tgb200_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _history_rows(self, first, count):
+        out = np.empty((count, _lib.HIST_COLS), dtype=np.float32)
+        if count:
+            _lib.check(self._lib.tgb200_get_history(self._h, first, count, _lib.ptr(out), None))
+        return out
+
+    def _exchange_tensor(self):
+        """torch view of the device exchange buffer (for torch.distributed.all_reduce)."""
+        import torch
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_exchange_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
+
+        class _Wrap:
+            __cuda_array_interface__ = {
+                "shape": (n.value,), "typestr": "<f4", "data": (p.value, False), "version": 3, "strides": None}
+        return torch.as_tensor(_Wrap(), device=f"cuda:{self._cfg.device}")
+
+    def _run(self, n_steps, lr):
+        if n_steps <= 0:
+            return
+        if not self._sharded:
+            _lib.check(self._lib.tgb200_run(self._h, n_steps, lr, None))
+            return
+        import torch
+        import torch.distributed as dist
+        buf = self._exchange_tensor()
+        stream = torch.cuda.current_stream(self._cfg.device).cuda_stream
+        for _ in range(n_steps):
+            _lib.check(self._lib.tgb200_step_begin(self._h, ctypes.c_void_p(stream)))
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._pg)      # the one exchange per step
+            _lib.check(self._lib.tgb200_step_end(self._h, lr, ctypes.c_void_p(stream)))
+
+    def train(self, num_epochs, learning_rate=0.1, print_each=100, val_each=None):
+        """mapping_optimizer.py:358-408.  Returns (softmax(M) as (N, V) f32 ndarray, history)."""
+        import logging
+        if print_each:
+            logging.info(f"Printing scores every {print_each} epochs.")
+        training_history = {key: [] for key in _HIST_KEYS + _VAL_KEYS}
+        first = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
+        first = first.value
+        lr = float(learning_rate)
+
+        t = 0
+        while t < num_epochs:
+            if val_each is not None:
+                chunk = 1
+            elif print_each:
+                chunk = min(num_epochs - t, print_each - (t % print_each))
+            else:
+                chunk = num_epochs - t
+            self._run(chunk, lr)
+            if print_each and t % print_each == 0:
+                print(format_terms(self._history_rows(first + t, 1)[0]))
+            if val_each is not None and t % val_each == 0:
+                vals = np.zeros(4, dtype=np.float32)
+                _lib.check(self._lib.tgb200_validation_terms(self._h, _lib.ptr(vals), None))
+                for k, x in zip(_VAL_KEYS, vals):
+                    training_history[k].append(float(x))
+            t += chunk
+
+        rows = self._history_rows(first, num_epochs)
+        training_history["total_loss"] = [np.array(x, dtype=np.float32) for x in rows[:, 0]]   # 0-d ndarrays (:390)
+        for c, key in enumerate(_HIST_KEYS[1:], start=1):
+            training_history[key] = [float(x) for x in rows[:, c]]
+        self.history_matrix = rows
+        output = np.empty((self.n_cells, self.n_voxels), dtype=np.float32)
+        _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(output), None))
+        return output, training_history
+
+    # --- extras beyond the reference surface -------------------------------------------
+    def state(self):
+        """(M, m, v, step): checkpoint of the optimizer (the reference stubs resume, :151-153)."""
+        M = np.empty((self.n_cells, self.n_voxels), dtype=np.float32)
+        m = np.empty_like(M)
+        v = np.empty_like(M)
+        step = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_get_state(self._h, _lib.ptr(M), _lib.ptr(m), _lib.ptr(v), ctypes.byref(step), None))
+        return M, m, v, step.value
+
+    def load_state(self, M, m, v, step):
+        M, m, v = (np.ascontiguousarray(x, dtype=np.float32) for x in (M, m, v))
+        _lib.check(self._lib.tgb200_set_state(self._h, _lib.ptr(M), _lib.ptr(m), _lib.ptr(v), int(step), None))
+
+    def project(self, X):
+        """softmax(M)^T @ X on the device (project_genes' GEMM, tangram/utils.py:368)."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        if X.shape[0] != self.n_cells:
+            raise ValueError("X must have one row per cell")
+        out = np.empty((self.n_voxels, X.shape[1]), dtype=np.float32)
+        _lib.check(self._lib.tgb200_project(self._h, _lib.ptr(X), X.shape[1], _lib.ptr(out), None))
+        return out
+
+    def kernel_launches(self):
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+
+def shard_rows(n_cells, rank, world):
+    """Contiguous cell-row block of `rank`: balanced to within one row."""
+    base, rem = divmod(n_cells, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)

@@ -1,0 +1,234 @@
+"""
+`map_cells_to_space` with the reference's signature and output contract
+(/root/reference/tangram/mapping_utils.py:141-428), hosted over the B200 Mapper.
+AnnData in, AnnData out (duck-typed: `anndata` is optional).  `pp_adatas` and
+`adata_to_cluster_expression` are the small host-side preparations this entry needs
+(:20-139); squidpy's neighbour graph must be supplied by the caller in
+`adata_sp.obsp` (scipy CSR), as squidpy itself would leave it.
+"""
+import logging
+
+import numpy as np
+import pandas as pd
+
+from . import mapping_optimizer as mo
+from . import spatial_weights as sw
+from .adata import make_adata
+
+
+def _dense_f32(X):
+    if hasattr(X, "toarray"):
+        return np.asarray(X.toarray(), dtype=np.float32)
+    if isinstance(X, np.ndarray):
+        return np.asarray(X, dtype=np.float32)     # the reference calls .toarray() here (:262, latent bug)
+    logging.error("AnnData X has unrecognized type: {}".format(type(X)))
+    raise NotImplementedError
+
+
+def annotate_gene_sparsity(adata):
+    """tangram/utils.py:46-60: var['sparsity'] = 1 - fraction of non-zero observations."""
+    mask = adata.X != 0
+    frac = np.asarray(mask.sum(axis=0)).reshape(-1) / adata.n_obs
+    adata.var["sparsity"] = 1 - frac
+
+
+def one_hot_encoding(labels):
+    """tangram/utils.py:105-123: one column per unique label, in order of first appearance."""
+    labels = pd.Series(labels).reset_index(drop=True)
+    return pd.DataFrame({u: (labels == u).astype(int) for u in labels.unique()})
+
+
+def pp_adatas(adata_sc, adata_sp, genes=None, gene_to_lowercase=True):
+    """mapping_utils.py:20-100 (gene intersection + density priors).  The squidpy neighbour
+    graph (:95-100) is not computed here: pass it in adata_sp.obsp."""
+    for ad in (adata_sc, adata_sp):
+        keep = np.asarray((ad.X != 0).sum(axis=0)).reshape(-1) >= 1        # sc.pp.filter_genes(min_cells=1)
+        if not keep.all():
+            sub = ad[:, keep]
+            ad.X, ad.var = sub.X, sub.var
+    if genes is None:
+        genes = adata_sc.var.index
+    if gene_to_lowercase:
+        adata_sc.var.index = [g.lower() for g in adata_sc.var.index]
+        adata_sp.var.index = [g.lower() for g in adata_sp.var.index]
+        genes = list(g.lower() for g in genes)
+    adata_sc.var_names_make_unique()
+    adata_sp.var_names_make_unique()
+    genes = list(set(genes) & set(adata_sc.var.index) & set(adata_sp.var.index))
+    adata_sc.uns["training_genes"] = genes
+    adata_sp.uns["training_genes"] = genes
+    logging.info("{} training genes are saved in `uns``training_genes` of both single cell and spatial Anndatas.".format(len(genes)))
+    overlap = np.sort(list(set(adata_sc.var.index) & set(adata_sp.var.index))).tolist()
+    adata_sc.uns["overlap_genes"] = overlap
+    adata_sp.uns["overlap_genes"] = overlap
+    logging.info("{} overlapped genes are saved in `uns``overlap_genes` of both single cell and spatial Anndatas.".format(len(overlap)))
+    n = adata_sp.X.shape[0]
+    adata_sp.obs["uniform_density"] = np.ones(n) / n
+    counts = np.array(adata_sp.X.sum(axis=1)).squeeze()
+    adata_sp.obs["rna_count_based_density"] = counts / np.sum(counts)
+
+
+def adata_to_cluster_expression(adata, cluster_label, scale=True, add_density=True):
+    """mapping_utils.py:103-139: one observation per cluster (sum if scale else mean)."""
+    try:
+        value_counts = adata.obs[cluster_label].value_counts(normalize=True)
+    except KeyError:
+        raise ValueError("Provided label must belong to adata.obs.")
+    unique_labels = value_counts.index
+    new_obs = pd.DataFrame({cluster_label: unique_labels})
+    new_obs.index = new_obs.index.astype(str)
+    X_new = np.empty((len(unique_labels), adata.shape[1]))
+    lab = np.asarray(adata.obs[cluster_label])
+    X = adata.X
+    for i, l in enumerate(unique_labels):
+        rows = X[np.nonzero(lab == l)[0]]
+        X_new[i] = np.asarray(rows.sum(axis=0) if scale else rows.mean(axis=0)).reshape(-1)
+    ret = make_adata(X=X_new, obs=new_obs, var=adata.var.copy(), uns=adata.uns)
+    if add_density:
+        ret.obs["cluster_density"] = ret.obs[cluster_label].map(lambda i: value_counts[i])
+    return ret
+
+
+def map_cells_to_space(
+    adata_sc,
+    adata_sp,
+    cv_train_genes=None,
+    cluster_label=None,
+    mode="cells",
+    device="cuda:0",
+    learning_rate=0.1,
+    num_epochs=1000,
+    scale=True,
+    lambda_d=0,
+    lambda_g1=1,
+    lambda_g2=0,
+    lambda_r=0,
+    lambda_l1=0,
+    lambda_l2=0,
+    lambda_count=1,
+    lambda_f_reg=1,
+    target_count=None,
+    lambda_neighborhood_g1=0,
+    lambda_ct_islands=0,
+    lambda_getis_ord=0,
+    lambda_moran=0,
+    lambda_geary=0,
+    random_state=None,
+    verbose=True,
+    density_prior="rna_count_based",
+    precision="fp32",
+):
+    """Same contract as the reference (mapping_utils.py:141-428); `device` must be CUDA.
+    `precision` ("fp32" | "bf16") is the only added keyword."""
+    # --- argument validation, same order and messages as :206-229
+    if lambda_g1 == 0:
+        raise ValueError("lambda_g1 cannot be 0.")
+    if (type(density_prior) is str) and (density_prior not in ["rna_count_based", "uniform", None]):
+        raise ValueError("Invalid input for density_prior.")
+    if density_prior is not None and (lambda_d == 0 or lambda_d is None):
+        lambda_d = 1
+    if lambda_d > 0 and density_prior is None:
+        raise ValueError("When lambda_d is set, please define the density_prior.")
+    if mode not in ["clusters", "cells", "constrained"]:
+        raise ValueError('Argument "mode" must be "cells", "clusters" or "constrained')
+    if mode == "clusters" and cluster_label is None:
+        raise ValueError("A cluster_label must be specified if mode is 'clusters'.")
+    if mode == "constrained" and not all([target_count, lambda_f_reg, lambda_count]):
+        raise ValueError("target_count, lambda_f_reg and lambda_count must be specified if mode is 'constrained'.")
+    if mode == "constrained":
+        # MapperConstrained (mapping_optimizer.py:411-639) is outside the accelerated path
+        raise NotImplementedError("mode='constrained' is not accelerated by tangram_b200; use the reference")
+
+    if mode == "clusters":
+        adata_sc = adata_to_cluster_expression(adata_sc, cluster_label, scale, add_density=True)
+
+    for ad in (adata_sc, adata_sp):                                              # :237-241
+        if not set(["training_genes", "overlap_genes"]).issubset(set(ad.uns.keys())):
+            raise ValueError("Missing tangram parameters. Run `pp_adatas()`.")
+    assert list(adata_sp.uns["training_genes"]) == list(adata_sc.uns["training_genes"])
+
+    if cv_train_genes is None:                                                   # :246-254
+        training_genes = adata_sc.uns["training_genes"]
+    elif set(cv_train_genes).issubset(set(adata_sc.uns["training_genes"])):
+        training_genes = cv_train_genes
+    else:
+        raise ValueError("Given training genes list should be subset of two AnnDatas.")
+
+    logging.info("Allocate tensors for mapping.")
+    S = _dense_f32(adata_sc[:, training_genes].X)                                # :259-275
+    G = _dense_f32(adata_sp[:, training_genes].X)
+    if not S.any(axis=0).all() or not G.any(axis=0).all():
+        raise ValueError("Genes with all zero values detected. Run `pp_adatas()`.")
+
+    d_source = None                                                              # :280-307
+    d_str = density_prior
+    if type(density_prior) is np.ndarray:
+        d_str = "customized"
+    if isinstance(density_prior, str) and density_prior == "rna_count_based":
+        density_prior = adata_sp.obs["rna_count_based_density"]
+    elif isinstance(density_prior, str) and density_prior == "uniform":
+        density_prior = adata_sp.obs["uniform_density"]
+    if mode == "cells":
+        d = density_prior
+    if mode == "clusters":
+        d_source = np.array(adata_sc.obs["cluster_density"])
+        if density_prior is None:
+            d = adata_sp.obs["uniform_density"]
+            d_str = "uniform"
+        else:
+            d = density_prior
+        if lambda_d is None or lambda_d == 0:
+            lambda_d = 1
+
+    print_each = 100 if verbose else None
+
+    voxel_weights, neighborhood_filter, ct_encode, spatial_weights = None, None, None, None   # :317-329
+    if lambda_neighborhood_g1 > 0:
+        voxel_weights = sw.spatial_weights(adata_sp, standardized=True, self_inclusion=True)
+    if lambda_ct_islands > 0:
+        if cluster_label not in adata_sc.obs.keys():
+            raise ValueError("cluster_label must be specified for the cell type island extension.")
+        neighborhood_filter = sw.spatial_weights(adata_sp, standardized=False, self_inclusion=False)
+        ct_encode = one_hot_encoding(adata_sc.obs[cluster_label]).values
+    if lambda_moran > 0 or lambda_geary > 0:
+        raise NotImplementedError("lambda_moran / lambda_geary are not supported by tangram_b200")
+    if lambda_getis_ord > 0:
+        spatial_weights = sw.spatial_weights(adata_sp, standardized=False, self_inclusion=True)
+
+    hyperparameters = {
+        "lambda_d": lambda_d, "lambda_g1": lambda_g1, "lambda_g2": lambda_g2, "lambda_r": lambda_r,
+        "lambda_l1": lambda_l1, "lambda_l2": lambda_l2, "d_source": d_source,
+        "lambda_neighborhood_g1": lambda_neighborhood_g1, "voxel_weights": voxel_weights,
+        "lambda_ct_islands": lambda_ct_islands, "neighborhood_filter": neighborhood_filter,
+        "ct_encode": ct_encode, "lambda_getis_ord": lambda_getis_ord, "spatial_weights": spatial_weights,
+    }
+    logging.info("Begin training with {} genes and {} density_prior in {} mode...".format(len(training_genes), d_str, mode))
+    mapper = mo.Mapper(S=S, G=G, d=None if d is None else np.asarray(d, dtype=np.float32), device=device,
+                       random_state=random_state, precision=precision, **hyperparameters)
+    mapping_matrix, training_history = mapper.train(
+        learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
+
+    logging.info("Saving results..")
+    adata_map = make_adata(X=mapping_matrix, obs=adata_sc[:, training_genes].obs.copy(),
+                           var=adata_sp[:, training_genes].obs.copy())
+
+    # per-gene training score (:401-410): softmax(M)^T S on the device instead of a host GEMM
+    G_predicted = mapper.project(S)
+    num = (G * G_predicted).sum(axis=0)
+    den = np.linalg.norm(G, axis=0) * np.linalg.norm(G_predicted, axis=0)
+    df_cs = pd.DataFrame(num / den, list(training_genes), columns=["train_score"])
+    df_cs = df_cs.sort_values(by="train_score", ascending=False)
+    adata_map.uns["train_genes_df"] = df_cs
+
+    annotate_gene_sparsity(adata_sc)                                             # :412-424
+    annotate_gene_sparsity(adata_sp)
+    adata_map.uns["train_genes_df"]["sparsity_sc"] = adata_sc[:, training_genes].var.sparsity
+    adata_map.uns["train_genes_df"]["sparsity_sp"] = adata_sp[:, training_genes].var.sparsity
+    adata_map.uns["train_genes_df"]["sparsity_diff"] = (
+        adata_sp[:, training_genes].var.sparsity - adata_sc[:, training_genes].var.sparsity)
+    adata_map.uns["training_history"] = training_history
+    try:      # keeps M resident on the device for project_genes (not part of `uns`: stays serialisable)
+        adata_map._tgb200_mapper = mapper
+    except Exception:  # noqa: BLE001
+        pass
+    return adata_map

@@ -1,0 +1,199 @@
+"""Parity of the CUDA path (through the C-ABI) against golden vectors produced by the real
+reference and against the oracle on seeded inputs.  Tolerances: the north_star asks for 1e-4
+relative on the final mapping matrix and on the loss trajectory (fp32 arithmetic)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle.tangram_oracle import OracleMapper, grid_graph, spatial_weights_from_graph, synthetic_inputs
+from tests.helpers import GOLDEN_CASES, load_golden, max_rel, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+def _mapper(**kw):
+    from tangram_b200 import Mapper
+    return Mapper(device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_one_step(name):
+    kw, g = load_golden(name)
+    m = _mapper(M0=g["M0"], **kw)
+    m.train(1, learning_rate=0.1, print_each=None)
+    M1, mom1, mom2, step = m.state()
+    assert step == 1
+    assert rel_fro(M1, g["M1"]) < 1e-5
+    assert abs(float(m.history_matrix[0, 0]) - g["total_loss"][0]) <= 2e-6 * max(1.0, abs(g["total_loss"][0]))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_trajectory_and_final_mapping(name):
+    kw, g = load_golden(name)
+    m = _mapper(M0=g["M0"], **kw)
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        out, hist = m.train(int(g["epochs"]), learning_rate=0.1, print_each=10)
+    tl = np.array([float(x) for x in hist["total_loss"]])
+    assert max_rel(tl, g["total_loss"]) < 1e-4
+    assert max_rel(hist["main_loss"], g["main_loss"]) < 1e-4
+    for k in ("vg_reg", "kl_reg", "entropy_reg"):
+        a, b = np.array(hist[k], dtype=np.float64), g[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        if not np.isnan(b).all():
+            assert max_rel(a[~np.isnan(b)], b[~np.isnan(b)]) < 1e-3
+    assert out.dtype == np.float32 and out.shape == g["output"].shape
+    assert rel_fro(out, g["output"]) < 1e-4
+    assert isinstance(hist["total_loss"][0], np.ndarray) and hist["total_loss"][0].shape == ()
+    assert isinstance(hist["main_loss"][0], float)
+    assert len(hist["total_loss"]) == int(g["epochs"]) and hist["val_total_loss"] == []
+    # the reference's print line (mapping_optimizer.py:300-307), epoch 0
+    assert buf.getvalue().splitlines()[0] == str(g["printed"]).splitlines()[0]
+    assert len(buf.getvalue().splitlines()) == len(str(g["printed"]).splitlines())
+
+
+@pytest.mark.parametrize("shape", [(1000, 257, 130), (777, 1000, 96), (2048, 512, 256)])
+def test_oracle_parity_ragged_shapes(shape):
+    """Shapes that are not multiples of any tile size; 10 steps at <= 1e-5, loss at 1e-5."""
+    N, V, K = shape
+    inp = synthetic_inputs(N, V, K, seed=N + V)
+    o = OracleMapper(inp["S"], inp["G"], d=inp["d"], lambda_d=1.0, random_state=42)
+    M0 = o.M.numpy().copy()
+    oo, oh = o.train(10, print_each=None)
+    m = _mapper(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, M0=M0)
+    out, hist = m.train(10, print_each=None)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < 1e-5
+    assert rel_fro(out, oo) < 1e-5
+    assert np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_oracle_parity_all_terms_medium():
+    N, V, K, T = 1500, 400, 200, 8
+    inp = synthetic_inputs(N, V, K, seed=2, n_types=T)
+    conn, dist = grid_graph(V)
+    kw = dict(
+        S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, lambda_g2=0.5, lambda_r=1e-3, lambda_l1=1e-7,
+        lambda_l2=1e-7, lambda_neighborhood_g1=0.96, lambda_ct_islands=0.17, lambda_getis_ord=0.71,
+        voxel_weights=spatial_weights_from_graph(conn, dist, True, True),
+        neighborhood_filter=spatial_weights_from_graph(conn, dist, False, False),
+        spatial_weights=spatial_weights_from_graph(conn, dist, False, True),
+        ct_encode=inp["ct_encode"])
+    o = OracleMapper(random_state=7, **kw)
+    M0 = o.M.numpy().copy()
+    oo, oh = o.train(15, print_each=None)
+    m = _mapper(M0=M0, **kw)
+    out, hist = m.train(15, print_each=None)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < 1e-4
+    assert rel_fro(out, oo) < 1e-4
+    # printed terms of the last epoch agree
+    last = o.terms_history[-1]
+    row = m.history_matrix[-1]
+    for col, key in ((7, "gv_neighborhood_sim"), (8, "ct_island_penalty"), (9, "getis_ord_sim")):
+        assert abs(row[col] - last[key]) < 1e-4 * max(1.0, abs(last[key]))
+
+
+def test_clusters_mode_large_voxels():
+    """small-N / large-V regime (BASELINE config 4, scaled down)."""
+    N, V, K = 48, 5000, 300
+    inp = synthetic_inputs(N, V, K, seed=4, clusters=True)
+    o = OracleMapper(inp["S"], inp["G"], d=inp["d"], d_source=inp["d_source"], lambda_d=1.0, random_state=3)
+    M0 = o.M.numpy().copy()
+    oo, oh = o.train(10, print_each=None)
+    m = _mapper(S=inp["S"], G=inp["G"], d=inp["d"], d_source=inp["d_source"], lambda_d=1.0, M0=M0)
+    out, hist = m.train(10, print_each=None)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < 1e-4
+    assert rel_fro(out, oo) < 1e-4
+
+
+def test_reference_draw_is_reproduced():
+    """random_state -> the same M0 bits as the reference draw (mapping_optimizer.py:147-157)."""
+    inp = synthetic_inputs(64, 40, 16, seed=0)
+    m = _mapper(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, random_state=42)
+    M, _, _, step = m.state()
+    np.random.seed(42)
+    ref = np.random.normal(0, 1, (64, 40)).astype(np.float32)
+    assert step == 0 and np.array_equal(M, ref)
+
+
+def test_determinism_and_resume():
+    """Same inputs -> bit-identical results; 12 steps == 5 steps + checkpoint + 7 steps."""
+    inp = synthetic_inputs(900, 300, 150, seed=8)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, random_state=5)
+    a, ha = _mapper(**kw).train(12, print_each=None)
+    b, hb = _mapper(**kw).train(12, print_each=None)
+    assert np.array_equal(a, b)
+    assert np.array_equal(np.array(ha["total_loss"]), np.array(hb["total_loss"]))
+    m1 = _mapper(**kw)
+    m1.train(5, print_each=None)
+    st = m1.state()
+    m2 = _mapper(**kw)
+    m2.load_state(*st)
+    c, _ = m2.train(7, print_each=None)
+    assert np.array_equal(a, c)
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 size (10k x 1k x 1k): size-independent properties + oracle loss at step 0."""
+    N, V, K = 10000, 1000, 1000
+    inp = synthetic_inputs(N, V, K, seed=0)
+    m = _mapper(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, random_state=42)
+    out, hist = m.train(30, print_each=None)
+    tl = np.array([float(x) for x in hist["total_loss"]])
+    assert np.all(np.isfinite(tl)) and tl[-1] < tl[0]                # the optimiser descends
+    assert np.all(np.diff(hist["main_loss"]) > -1e-4)                # gene score rises (monotone here)
+    assert out.min() >= 0 and np.allclose(out.sum(axis=1), 1.0, atol=2e-5)
+    np.random.seed(42)
+    M0 = np.random.normal(0, 1, (N, V))
+    o = OracleMapper(inp["S"], inp["G"], d=inp["d"], lambda_d=1.0, M0=M0)
+    terms, _ = o.loss_and_grad(need_grad=False)
+    assert abs(terms["total_loss"] - tl[0]) < 1e-5 * max(1.0, abs(tl[0]))
+    # project == softmax(M)^T X
+    X = np.random.default_rng(0).random((N, 37)).astype(np.float32)
+    assert rel_fro(m.project(X), out.T.astype(np.float64) @ X) < 1e-5
+
+
+def test_validation_terms_match_oracle():
+    inp = synthetic_inputs(400, 120, 60, seed=6)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0)
+    o = OracleMapper(random_state=9, **kw)
+    M0 = o.M.numpy().copy()
+    _, oh = o.train(4, print_each=None, val_each=2)
+    m = _mapper(M0=M0, **kw)
+    _, hist = m.train(4, print_each=None, val_each=2)
+    for k in ("val_total_loss", "val_gene_sim", "val_sp_sparsity_weighted_sim", "val_entropy"):
+        assert len(hist[k]) == len(oh[k]) == 2
+        assert max_rel(hist[k], oh[k]) < 1e-4
+
+
+def test_map_cells_to_space_api_end_to_end():
+    import pandas as pd
+    import tangram_b200 as tg
+    N, V, K = 300, 80, 50
+    inp = synthetic_inputs(N, V, K, seed=12)
+    genes = [f"Gene{i}" for i in range(K)]
+    ad_sc = tg.MiniAnnData(X=inp["S"].copy(), obs=pd.DataFrame({"lab": [f"t{i % 3}" for i in range(N)]},
+                           index=[f"c{i}" for i in range(N)]), var=pd.DataFrame(index=genes))
+    ad_sp = tg.MiniAnnData(X=inp["G"].copy(), obs=pd.DataFrame({"x": np.arange(V)}, index=[f"v{i}" for i in range(V)]),
+                           var=pd.DataFrame(index=genes))
+    tg.pp_adatas(ad_sc, ad_sp)
+    ad_map = tg.map_cells_to_space(ad_sc, ad_sp, device="cuda:0", num_epochs=20, random_state=3, verbose=False)
+    assert ad_map.X.shape == (N, V)
+    df = ad_map.uns["train_genes_df"]
+    assert list(df.columns) == ["train_score", "sparsity_sc", "sparsity_sp", "sparsity_diff"]
+    assert df["train_score"].is_monotonic_decreasing and len(df) == K
+    assert set(ad_map.uns["training_history"]) >= {"total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg"}
+    # same answer as the oracle fed the same way
+    tr = ad_sc.uns["training_genes"]
+    S = np.asarray(ad_sc[:, tr].X, dtype=np.float32)
+    G = np.asarray(ad_sp[:, tr].X, dtype=np.float32)
+    o = OracleMapper(S, G, d=np.asarray(ad_sp.obs["rna_count_based_density"], dtype=np.float32), lambda_d=1, random_state=3)
+    oo, _ = o.train(20, print_each=None)
+    assert rel_fro(ad_map.X, oo) < 1e-4
+    ad_ge = tg.project_genes(ad_map, ad_sc)
+    assert ad_ge.X.shape == (V, K) and ad_ge.var["is_training"].all()
+    assert rel_fro(ad_ge.X, ad_map.X.T.astype(np.float64) @ np.asarray(ad_sc.X)) < 1e-5
+    # clusters mode runs and returns one row per cluster
+    ad_map_c = tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters", cluster_label="lab", device="cuda:0",
+                                     num_epochs=10, random_state=3, verbose=False)
+    assert ad_map_c.X.shape == (3, V)
