@@ -173,6 +173,11 @@ TGB200_API int tgb200_profile_step(tgb200_mapper* h, float learning_rate, void* 
 /* Algorithmic bytes and flops of one iteration for this handle's shape. */
 TGB200_API int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops);
 
+/* Diagnostics: copy an internal device buffer to HOST memory after a step.  name: "Y" (V x Ke),
+ * "dY" (V x Ke), "rdot" (n_cells), "Sx" (n_cells x Ke), "shape" (Ke, ld, fwd_splits, r_parts).
+ * out_host may be NULL to query the size (*n). */
+TGB200_API int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* out_host, int64_t cap, int64_t* n);
+
 TGB200_API const char* tgb200_last_error(void);
 TGB200_API const char* tgb200_version(void);
 

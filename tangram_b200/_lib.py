@@ -62,6 +62,7 @@ SIGNATURES = {
     "tgb200_profile_step": (ctypes.c_int, [_P, ctypes.c_float, _P, ctypes.POINTER(ctypes.c_char_p), _F,
                                            ctypes.c_int32, _I32]),
     "tgb200_algorithmic_cost": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "tgb200_debug_buffer": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_int64, _I64]),
     "tgb200_last_error": (ctypes.c_char_p, []),
     "tgb200_version": (ctypes.c_char_p, []),
 }

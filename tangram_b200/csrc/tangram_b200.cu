@@ -84,7 +84,7 @@ struct tgb200_mapper {
   DevBuf<float> d, dsrc;
   DevBuf<RowStat> stats;
   DevBuf<float> rowaux, rdot, rpart;
-  int r_parts = 0;
+  int r_parts = 0, rd_splits = 1;
   // forward / loss
   int fwd_splits = 1;
   DevBuf<float> Ypart;          // splits x V x Ke (only when splits > 1)
@@ -194,7 +194,8 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
   }
   A(h->Y.alloc(vk + 4)); A(h->dY.alloc(vk));
-  h->r_parts = (int)ceil_div(h->Ke, h->bf16 ? TC_RDOT_BN : SG_BN) * (h->bf16 ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1);
+  h->rd_splits = h->bf16 ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
+  h->r_parts = (int)ceil_div(h->Ke, h->bf16 ? TC_RDOT_BN : SG_BN) * h->rd_splits;
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
   h->nchunk = (int)ceil_div(h->V, kLossRows);
@@ -576,7 +577,7 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
 
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
   if (h->bf16) {
-    CKS(tc_rowdot(h->tc, h->Pb.p, h->dYb.p, h->Sx.p, h->rpart.p, h->N, h->V, h->Ke, h->ld, s, g_err, sizeof(g_err)));
+    CKS(tc_rowdot(h->tc, h->Pb.p, h->dYb.p, h->Sxb.p, h->rpart.p, h->N, h->V, h->Ke, h->ld, h->rd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_rowdot");
   } else {
     GemmArgs g;
@@ -798,6 +799,34 @@ extern "C" int tgb200_profile_step(tgb200_mapper* h, float lr, void* stream, con
   for (auto e : t.ev) cudaEventDestroy(e);
   *n = cnt;
   return st;
+}
+
+extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* out_host, int64_t cap, int64_t* n) {
+  if (!h || !name || !n) return fail(TGB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const std::string nm(name);
+  const float* src = nullptr;
+  int64_t cnt = 0;
+  const int64_t vk = (int64_t)h->V * h->Ke;
+  if (nm == "Y") { src = h->Y.p; cnt = vk; }
+  else if (nm == "dY") { src = h->dY.p; cnt = vk; }
+  else if (nm == "rdot") { src = h->rdot.p; cnt = h->N; }
+  else if (nm == "Sx") { src = h->Sx.p; cnt = (int64_t)h->N * h->Ke; }
+  else if (nm == "shape") {   // Ke, ld, fwd_splits, r_parts
+    *n = 4;
+    if (!out_host) return TGB200_OK;
+    if (cap < 4) return fail(TGB200_ERR_INVALID, "cap < 4");
+    out_host[0] = (float)h->Ke; out_host[1] = (float)h->ld; out_host[2] = (float)h->fwd_splits; out_host[3] = (float)h->r_parts;
+    *n = 4;
+    return TGB200_OK;
+  } else return fail(TGB200_ERR_INVALID, "unknown debug buffer '%s'", name);
+  *n = cnt;
+  if (out_host) {
+    if (cap < cnt) return fail(TGB200_ERR_INVALID, "buffer '%s' needs %lld floats", name, (long long)cnt);
+    CK(cudaMemcpy(out_host, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return TGB200_OK;
 }
 
 extern "C" int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops) {

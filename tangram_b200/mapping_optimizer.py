@@ -303,6 +303,14 @@ class Mapper:
         _lib.check(self._lib.tgb200_project(self._h, _lib.ptr(X), X.shape[1], _lib.ptr(out), None))
         return out
 
+    def _debug(self, name):
+        """Diagnostics: internal device buffer by name (see tgb200_debug_buffer)."""
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_debug_buffer(self._h, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.empty(max(n.value, 4), dtype=np.float32)
+        _lib.check(self._lib.tgb200_debug_buffer(self._h, name.encode(), _lib.ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value]
+
     def kernel_launches(self):
         n = ctypes.c_int64()
         _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))

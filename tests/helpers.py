@@ -41,3 +41,15 @@ def load_reference_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def assert_same_print(ours, ref):
+    """The reference's print line `name: value, name: value` (mapping_optimizer.py:300-307):
+    same names in the same order; values equal to the printed 3 decimals up to one unit in the
+    last printed digit or 1e-6 relative (an fp32 sum differs in its 8th digit)."""
+    a = [x.split(": ") for x in ours.split(", ")]
+    b = [x.split(": ") for x in ref.split(", ")]
+    assert [x[0] for x in a] == [x[0] for x in b], (ours, ref)
+    for (_, va), (_, vb) in zip(a, b):
+        va, vb = float(va), float(vb)
+        assert abs(va - vb) <= 0.0011 + 1e-6 * abs(vb), (ours, ref)

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle.tangram_oracle import OracleMapper, synthetic_inputs
-from tests.helpers import GOLDEN_CASES, REFERENCE_FILE, load_golden, load_reference_module, max_rel, rel_fro
+from tests.helpers import assert_same_print, GOLDEN_CASES, REFERENCE_FILE, load_golden, load_reference_module, max_rel, rel_fro
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -43,7 +43,7 @@ def test_oracle_matches_golden_trajectory(name):
     assert rel_fro(out, g["output"]) < 1e-4                         # final mapping matrix
     assert out.dtype == np.float32 and out.shape == g["output"].shape
     # printed lines: same text (mapping_optimizer.py:300-307)
-    assert buf.getvalue().splitlines()[0] == str(g["printed"]).splitlines()[0]
+    assert_same_print(buf.getvalue().splitlines()[0], str(g["printed"]).splitlines()[0])
 
 
 def test_oracle_float64_gradient_matches_finite_differences():

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.tangram_oracle import OracleMapper, grid_graph, spatial_weights_from_graph, synthetic_inputs
-from tests.helpers import GOLDEN_CASES, load_golden, max_rel, rel_fro
+from tests.helpers import assert_same_print, GOLDEN_CASES, load_golden, max_rel, rel_fro
 
 pytestmark = pytest.mark.gpu
 
@@ -49,7 +49,7 @@ def test_golden_trajectory_and_final_mapping(name):
     assert isinstance(hist["main_loss"][0], float)
     assert len(hist["total_loss"]) == int(g["epochs"]) and hist["val_total_loss"] == []
     # the reference's print line (mapping_optimizer.py:300-307), epoch 0
-    assert buf.getvalue().splitlines()[0] == str(g["printed"]).splitlines()[0]
+    assert_same_print(buf.getvalue().splitlines()[0], str(g["printed"]).splitlines()[0])
     assert len(buf.getvalue().splitlines()) == len(str(g["printed"]).splitlines())
 
 
