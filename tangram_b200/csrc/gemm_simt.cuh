@@ -20,7 +20,7 @@ constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16, SG_LD = 132, SG_THREADS = 25
 
 // Adam scalars of one step (torch/optim/adam.py single-tensor path, computed in double on the host)
 struct AdamScalars {
-  float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, bc2_sqrt, eps;
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, step_size, bc2_sqrt, eps, inv_bc2_sqrt;
 };
 
 __device__ __forceinline__ float adam_update(float x, float g, float& m, float& v, const AdamScalars& a) {

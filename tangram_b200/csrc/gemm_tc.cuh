@@ -6,8 +6,11 @@
 //   row-dot   r_i = <S_ext_i, (P dY_ext)_i>     A = P  (K-major),  B = dY_ext (MN-major), split over voxels
 //   backward  dP = S_ext dY_ext^T  -> softmax-Jacobian + Adam in the epilogue (A, B K-major)
 //
-// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Persistent, warp-specialised kernel: one CTA per SM loops over output tiles.
+//   warp 0      TMA producer: keeps the operand ring full across tile boundaries
+//   warp 1      TMEM allocator + MMA issuer: two accumulator buffers in TMEM, so the MMAs of tile i+1
+//               run while the epilogue warps drain tile i
+//   warps 2..   epilogue (TMEM lane quarter = warp_id % 4)
 #pragma once
 #include <cuda.h>
 #include <cstdio>
@@ -41,15 +44,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// L2 policy: operand tiles are re-read by many CTAs -> evict_last (CUTLASS TMA::CacheHintSm90::EVICT_LAST)
+constexpr uint64_t kPolicyEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(kPolicyEvictLast) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -127,118 +144,338 @@ struct OperandTile {
   }
 };
 
-// ---- epilogues (thread = one TMEM lane = one output row; 16 consecutive columns per call) ------
-struct TcEpiStore {
-  float* C; int ldc; size_t split_stride; int M, N;   // N = ldc extent guard
-  __device__ __forceinline__ void begin(int) {}
-  __device__ __forceinline__ void chunk(int row, int col, const float (&v)[16]) {
-    if (row >= M || col >= ldc) return;
-    float4* dst = reinterpret_cast<float4*>(C + (size_t)blockIdx.z * split_stride + (size_t)row * ldc + col);
+// ---- epilogues ------------------------------------------------------------------------------
+// Each epilogue warp owns TMEM lanes [32q, 32q+32) = output rows m0+32q.. of the tile.
+// run() is called once per warp after the accumulator is complete; `scratch` is the (now idle)
+// operand ring, 1024-byte aligned, at least 32 KB.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Coordinates of the work item an epilogue warp is draining.
+struct TileCoord {
+  int m0, n0;        // first output row / column of the tile
+  int tile_n;        // column-tile index
+  int tiles_n;       // number of column tiles
+  int split;         // k-split index
+};
+
+struct TcEpiStore {
+  float* C; int ldc; size_t split_stride; int M;
+  static constexpr int kStagingBytes = 0;
+  template <int BN, int NW>
+  __device__ __forceinline__ void prefetch_next(const TileCoord&, int, int, int) {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, uint32_t) {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, uint32_t) {
+    static_assert(NW == 4, "one warp per TMEM lane quarter");
+    const int row = t.m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      const int col = t.n0 + c;
+      if (row < M && col < ldc) {
+        float4* dst = reinterpret_cast<float4*>(C + (size_t)t.split * split_stride + (size_t)row * ldc + col);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+      }
+    }
   }
-  __device__ __forceinline__ void end(int) {}
 };
 
 struct TcEpiRowDot {
   const __nv_bfloat16* S; int lds; float* rpart; int M;
-  float acc;
-  __device__ __forceinline__ void begin(int) { acc = 0.f; }
-  __device__ __forceinline__ void chunk(int row, int col, const float (&v)[16]) {
-    if (row >= M || col >= lds) return;
-    const uint4* src = reinterpret_cast<const uint4*>(S + (size_t)row * lds + col);
+  static constexpr int kStagingBytes = 0;
+  template <int BN, int NW>
+  __device__ __forceinline__ void prefetch_next(const TileCoord&, int, int, int) {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, uint32_t) {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, uint32_t) {
+    static_assert(NW == 4, "one warp per TMEM lane quarter");
+    const int row = t.m0 + q * 32 + lane;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      const int col = t.n0 + c;
+      if (row < M && col < lds) {
+        const uint4* src = reinterpret_cast<const uint4*>(S + (size_t)row * lds + col);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const uint4 u = src[q];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int h = 0; h < 2; ++h) {
+          const uint4 u = src[h];
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-        acc = fmaf(v[q * 8 + 2 * e], __low2float(b), acc);
-        acc = fmaf(v[q * 8 + 2 * e + 1], __high2float(b), acc);
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+            acc = fmaf(v[h * 8 + 2 * e], __low2float(b), acc);
+            acc = fmaf(v[h * 8 + 2 * e + 1], __high2float(b), acc);
+          }
+        }
       }
     }
-  }
-  __device__ __forceinline__ void end(int row) {
-    if (row < M) rpart[((size_t)blockIdx.z * gridDim.x + blockIdx.x) * M + row] = acc;
+    if (row < M) rpart[((size_t)t.split * t.tiles_n + t.tile_n) * M + row] = acc;
   }
 };
+
+// Per-row constants of the backward epilogue: lse = exact log-sum-exp of the row (P_ij = exp(M_ij - lse)),
+// r = row-dot, h = sum_j P log P (entropy term only).
+struct __align__(16) RowConst { float lse, r, h, pad; };
 
 struct TcAdamArgs {
   float* Mp; float* mp; float* vp; int ld; int V;
-  const RowStat* stats; const float* rdot;
+  const RowConst* rowc;
   float lam_r, lam_l1, lam_l2;
   AdamScalars a;
+  // next iteration's forward operand and its per-row partial sums (see k_row_norm)
+  __nv_bfloat16* Pt;      // N x ld, Pt_ij = exp(Mnew_ij - lse_i)
+  float* zpart;           // [n_col_parts][N]
+  float* pxpart;          // or null
+  float* l1part;          // or null (then l2part is null too)
+  float* l2part;
 };
+
+// The three N x V state arrays are the HBM-bound part of the whole iteration (24 B/element), so
+// the epilogue is built around bytes in flight, not instructions: every warp stages its own
+// 32-row x 16-column sub-tiles of M, m, v into shared memory with cp.async (16 B per lane, one warp
+// instruction = 8 rows x 64 contiguous bytes), two sub-tiles deep (12 KB in flight per warp, 96 KB
+// per CTA), updates them in shared memory with one thread per row (matching the TMEM accumulator
+// layout; 16-byte chunks XOR-swizzled by row so both access patterns are bank-conflict free) and
+// streams them back with coalesced 128-bit stores.  All synchronisation is warp-local
+// (cp.async.wait_group + __syncwarp).
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(kPolicyEvictFirst) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void st_stream_hint(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(kPolicyEvictFirst) : "memory");
+}
+
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 struct TcEpiAdam {
   TcAdamArgs p; int M;
-  RowStat st; float r;
-  __device__ __forceinline__ void begin(int row) {
-    if (row < M) { st = p.stats[row]; r = p.rdot[row]; }
-  }
-  __device__ __forceinline__ float one(float x, float dp, float& m, float& v) const {
-    const float pr = softmax_prob(x, st);
-    float g = dp - r;
-    if (p.lam_r != 0.f) g -= p.lam_r * (((x - st.mx) - st.log_z) - st.h);
+  static constexpr int CW = 16;                            // columns per staged sub-tile
+  static constexpr int kArrayBytes = 32 * CW * 4;          // 32 rows x 16 floats = 2 KB
+  static constexpr int kBufBytes = 3 * kArrayBytes;        // M, m, v
+  static constexpr int kWarpBytes = 2 * kBufBytes;         // double buffered: 12 KB per warp
+  static constexpr int kStagingBytes = 8 * kWarpBytes;     // 8 epilogue warps
+  // 64-byte rows, 16-byte chunks XOR-swizzled so that both "thread = row" and "8 rows x 4 chunks per
+  // warp instruction" are bank-conflict free.
+  static __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+  // bf16-mode arithmetic: approximate MUFU ops (ex2, sqrt, rcp), ~2 ulp -- far below bf16 operand noise
+  __device__ __forceinline__ float one(float x, float dp, float& m, float& v, const RowConst& rc, float lse_l2e) const {
+    const float pr = fast_ex2(fmaf(x, 1.4426950408889634f, -lse_l2e));
+    float g = dp - rc.r;
+    if (p.lam_r != 0.f) g -= p.lam_r * ((x - rc.lse) - rc.h);
     g *= pr;
     if (p.lam_l1 != 0.f) g += p.lam_l1 * (float)((x > 0.f) - (x < 0.f));
     if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x;
-    return adam_update(x, g, m, v, p.a);
+    m = fmaf(g - m, p.a.one_minus_beta1, m);
+    v = fmaf(p.a.one_minus_beta2 * g, g, v * p.a.beta2);
+    const float denom = fmaf(fast_sqrt(v), p.a.inv_bc2_sqrt, p.a.eps);
+    return fmaf(-p.a.step_size * m, fast_rcp(denom), x);
   }
-  __device__ __forceinline__ void chunk(int row, int col, const float (&acc)[16]) {
-    if (row >= M || col >= p.V) return;
-    const size_t o = (size_t)row * p.ld + col;
-    float4* Mq = reinterpret_cast<float4*>(p.Mp + o);
-    float4* mq = reinterpret_cast<float4*>(p.mp + o);
-    float4* vq = reinterpret_cast<float4*>(p.vp + o);
-    float4 x[4], m[4], v[4];
+  // Pt for the next forward pass + this thread's (= this row's) partial sums
+  __device__ __forceinline__ float next_p(float xn, float lse_l2e, float& zs, float& pxs, float& l1s, float& l2s) const {
+    const float pt = fast_ex2(fmaf(xn, 1.4426950408889634f, -lse_l2e));
+    zs += pt;
+    if (p.pxpart) pxs = fmaf(pt, xn, pxs);
+    if (p.l1part) { l1s += fabsf(xn); l2s = fmaf(xn, xn, l2s); }
+    return pt;
+  }
+  // global -> shared (coalesced): lane handles rows sub + 8 i, 16-byte chunk j
+  __device__ __forceinline__ void prefetch(uint32_t buf, int row0, int col0, int lane) const {
+    const int sub = lane >> 2, j = lane & 3;
+    const int col = col0 + 4 * j;
+    if (col < p.ld) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { x[q] = Mq[q]; m[q] = mq[q]; v[q] = vq[q]; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = col + 4 * q;
-      if (c + 0 < p.V) x[q].x = one(x[q].x, acc[4 * q + 0], m[q].x, v[q].x);
-      if (c + 1 < p.V) x[q].y = one(x[q].y, acc[4 * q + 1], m[q].y, v[q].y);
-      if (c + 2 < p.V) x[q].z = one(x[q].z, acc[4 * q + 2], m[q].z, v[q].z);
-      if (c + 3 < p.V) x[q].w = one(x[q].w, acc[4 * q + 3], m[q].w, v[q].w);
+      for (int i = 0; i < 4; ++i) {
+        const int rl = sub + 8 * i;
+        const int row = row0 + rl;
+        if (row < M) {
+          const size_t o = (size_t)row * p.ld + col;
+          const uint32_t d = buf + swz(rl, j);
+          cp_async16(d, p.Mp + o);
+          cp_async16(d + kArrayBytes, p.mp + o);
+          cp_async16(d + 2 * kArrayBytes, p.vp + o);
+        }
+      }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { Mq[q] = x[q]; mq[q] = m[q]; vq[q] = v[q]; }
   }
-  __device__ __forceinline__ void end(int) {}
+  __device__ __forceinline__ void writeback(uint32_t buf, int row0, int col0, int lane) const {
+    const int sub = lane >> 2, j = lane & 3;
+    const int col = col0 + 4 * j;
+    if (col < p.ld) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = sub + 8 * i;
+        const int row = row0 + rl;
+        if (row < M) {
+          const size_t o = (size_t)row * p.ld + col;
+          const uint32_t sp = buf + swz(rl, j);
+          st_stream_hint(reinterpret_cast<float4*>(p.Mp + o), lds128(sp));
+          st_stream_hint(reinterpret_cast<float4*>(p.mp + o), lds128(sp + kArrayBytes));
+          st_stream_hint(reinterpret_cast<float4*>(p.vp + o), lds128(sp + 2 * kArrayBytes));
+        }
+      }
+    }
+  }
+  // DRAM -> L2 prefetch of the NEXT tile's M, m, v rows (this warp's 32 rows x COLS columns), one
+  // bulk prefetch per 256-byte row segment.  The cp.async loads of the next tile then hit L2, so the
+  // 96 KB of shared-memory staging is enough bytes in flight to run at HBM rate.
+  template <int BN, int NW>
+  __device__ __forceinline__ void prefetch_next(const TileCoord& t, int q, int ew, int lane) {
+    constexpr int COLS = BN / (NW / 4);
+    const int row = t.m0 + q * 32 + lane;
+    const int col = t.n0 + (ew >> 2) * COLS;
+    if (row < M && col < p.ld) {
+      const int ncol = min(COLS, p.ld - col);
+      const size_t o = (size_t)row * p.ld + col;
+      const uint32_t bytes = (uint32_t)ncol * 4u;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Mp + o), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.mp + o), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.vp + o), "r"(bytes) : "memory");
+    }
+  }
+  // Issued before the wait on the accumulator: the first two sub-tiles are already in flight when the
+  // MMAs of this tile retire.
+  template <int BN, int NW>
+  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, uint32_t staging) {
+    constexpr int COLS = BN / (NW / 4);
+    const uint32_t wbuf = staging + ew * kWarpBytes;
+    const int row0 = t.m0 + q * 32;
+    const int cbase = t.n0 + (ew >> 2) * COLS;
+    prefetch(wbuf, row0, cbase, lane);
+    cp_async_commit();
+    prefetch(wbuf + kBufBytes, row0, cbase + CW, lane);
+    cp_async_commit();
+  }
+  // one 16-column sub-tile, thread = row.  GUARD=false: all 16 columns are real voxels.
+  template <bool GUARD>
+  __device__ __forceinline__ void update_chunk(uint32_t buf, int lane, int row, int col0, const float (&acc)[16],
+                                               const RowConst& rc, float lse_l2e, float& zs, float& pxs, float& l1s,
+                                               float& l2s) const {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t sp = buf + swz(lane, j);
+      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
+      const int col = col0 + 4 * j;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+      if (!GUARD || col + 0 < p.V) { x.x = one(x.x, acc[4 * j + 0], m.x, v.x, rc, lse_l2e); p0 = next_p(x.x, lse_l2e, zs, pxs, l1s, l2s); }
+      if (!GUARD || col + 1 < p.V) { x.y = one(x.y, acc[4 * j + 1], m.y, v.y, rc, lse_l2e); p1 = next_p(x.y, lse_l2e, zs, pxs, l1s, l2s); }
+      if (!GUARD || col + 2 < p.V) { x.z = one(x.z, acc[4 * j + 2], m.z, v.z, rc, lse_l2e); p2 = next_p(x.z, lse_l2e, zs, pxs, l1s, l2s); }
+      if (!GUARD || col + 3 < p.V) { x.w = one(x.w, acc[4 * j + 3], m.w, v.w, rc, lse_l2e); p3 = next_p(x.w, lse_l2e, zs, pxs, l1s, l2s); }
+      sts128(sp, x);
+      sts128(sp + kArrayBytes, m);
+      sts128(sp + 2 * kArrayBytes, v);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+      pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
+      pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    // 16 bf16 = one 32-byte sector per row, written straight from the row-owning thread
+    uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  // ew = epilogue warp index (0..NW-1); TMEM lane quarter q; this warp owns columns [part*BN/parts, ...)
+  template <int BN, int NW>
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, uint32_t staging) {
+    constexpr int PARTS = NW / 4;
+    constexpr int COLS = BN / PARTS;
+    constexpr int NCHUNK = COLS / CW;
+    static_assert(NCHUNK >= 2, "prologue prefetches two sub-tiles");
+    const int part = ew >> 2;
+    const uint32_t wbuf = staging + ew * kWarpBytes;
+    const int row0 = t.m0 + q * 32;
+    const int row = row0 + lane;
+    const int cbase = t.n0 + part * COLS;
+    RowConst rc = {0.f, 0.f, 0.f, 0.f};
+    if (row < M) rc = p.rowc[row];
+    const float lse_l2e = rc.lse * 1.4426950408889634f;
+    float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      const uint32_t buf = wbuf + (c & 1) * kBufBytes;
+      const int col0 = cbase + c * CW;
+      if (c + 1 < NCHUNK) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      float acc[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * COLS + c * CW), acc);
+      if (row < M && col0 < p.ld) {
+        if (col0 + CW <= p.V) update_chunk<false>(buf, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+        else update_chunk<true>(buf, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+      }
+      __syncwarp();
+      writeback(buf, row0, col0, lane);
+      __syncwarp();
+      if (c + 2 < NCHUNK) prefetch(buf, row0, cbase + (c + 2) * CW, lane);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    if (row < M) {
+      const size_t o = ((size_t)t.tile_n * PARTS + part) * M + row;
+      p.zpart[o] = zs;
+      if (p.pxpart) p.pxpart[o] = pxs;
+      if (p.l1part) { p.l1part[o] = l1s; p.l2part[o] = l2s; }
+    }
+  }
 };
 
 // ---- the kernel -------------------------------------------------------------------------------
-// grid: x = N tiles, y = M tiles, z = k splits.  One output tile (128 x BN) per CTA.
-template <bool A_KMAJOR, bool B_KMAJOR, int BN, int STAGES, int MIN_CTAS, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, MIN_CTAS)
+// Work item w -> (split z, row tile, column tile), column tile fastest so that CTAs running at the
+// same time share A rows and stream B through L2.
+template <bool A_KMAJOR, bool B_KMAJOR, int BN, int STAGES, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          int k_total, int k_per_split, Epi epi) {
+          int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
   using TileB = OperandTile<B_KMAJOR, BN>;
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;   // power of two (BN is 128 or 256)
+  constexpr uint32_t kTmemCols = 2 * BN;     // two accumulator buffers (256 or 512 columns)
+  static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
   constexpr uint32_t kIdesc = make_idesc(TC_BM, BN, !A_KMAJOR, !B_KMAJOR);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
-  const int k_begin = blockIdx.z * k_per_split;
-  const int k_end = min(k_total, k_begin + k_per_split);
-  const int num_kb = (k_end > k_begin) ? (k_end - k_begin + TC_BK - 1) / TC_BK : 0;
+  const int total = tiles_m * tiles_n * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -250,56 +487,90 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * kStageBytes;
-        uint8_t* sb = sa + TileA::kBytes;
-        mbar_expect_tx(&full_bar[s], kStageBytes);
-        const int k0 = k_begin + kb * TC_BK;
-        TileA::load(&map_a, &full_bar[s], sa, m0, k0);
-        TileB::load(&map_b, &full_bar[s], sb, n0, k0);
+      uint32_t kbg = 0;                         // k-blocks issued so far (ring position)
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n0 = (w % tiles_n) * BN;
+        const int m0 = ((w / tiles_n) % tiles_m) * TC_BM;
+        const int z = w / (tiles_n * tiles_m);
+        const int k_begin = z * k_per_split;
+        const int k_end = min(k_total, k_begin + k_per_split);
+        const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + TileA::kBytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);
+          const int k0 = k_begin + kb * TC_BK;
+          TileA::load(&map_a, &full_bar[s], sa, m0, k0);
+          TileB::load(&map_b, &full_bar[s], sb, n0, k0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t kbg = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int z = w / (tiles_n * tiles_m);
+        const int k_begin = z * k_per_split;
+        const int k_end = min(k_total, k_begin + k_per_split);
+        const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
+        const int b = it & 1;
+        mbar_wait(&tempty_bar[b], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kStageBytes);
-        const uint32_t sb = sa + TileA::kBytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint32_t sb = sa + TileA::kBytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-          umma_bf16(tmem_base, TileA::desc(sa, k), TileB::desc(sb, k), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
-        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);  // accumulator complete
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+            umma_bf16(d_tmem, TileA::desc(sa, k), TileB::desc(sb, k), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);           // frees the smem stage when these MMAs retire
+        }
+        umma_commit(&tfull_bar[b]);             // accumulator of this tile complete
       }
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue =====
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    epi.begin(row);
-    if (num_kb > 0) {
-      mbar_wait(&tmem_full_bar, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      if (num_kb > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int ew = warp - 2;
+    const uint32_t staging = smem_u32(smem + STAGES * kStageBytes);
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      TileCoord t;
+      t.tile_n = w % tiles_n;
+      t.tiles_n = tiles_n;
+      t.n0 = t.tile_n * BN;
+      t.m0 = ((w / tiles_n) % tiles_m) * TC_BM;
+      t.split = w / (tiles_n * tiles_m);
+      const int b = it & 1;
+      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, staging);
+      {
+        const int wn = w + (int)gridDim.x;
+        if (wn < total) {
+          TileCoord tn;
+          tn.tile_n = wn % tiles_n;
+          tn.tiles_n = tiles_n;
+          tn.n0 = tn.tile_n * BN;
+          tn.m0 = ((wn / tiles_n) % tiles_m) * TC_BM;
+          tn.split = wn / (tiles_n * tiles_m);
+          epi.template prefetch_next<BN, EPI_WARPS>(tn, q, ew, lane);
+        }
       }
-      epi.chunk(row, n0 + c, v);
+      mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, staging);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[b]);
     }
-    epi.end(row);
   }
   tc_fence_before();
   __syncthreads();
@@ -313,6 +584,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcContext {
   PFN_encodeTiled encode = nullptr;
+  int num_sms = 148;
 };
 
 static inline int tc_init(TcContext& tc, char* err, size_t n) {
@@ -324,6 +596,9 @@ static inline int tc_init(TcContext& tc, char* err, size_t n) {
     return -2;
   }
   tc.encode = (PFN_encodeTiled)fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
   return 0;
 }
 
@@ -358,7 +633,7 @@ static inline int tc_check_launch(const char* name, char* err, size_t n) {
 }
 
 constexpr int TC_FWD_BN = 256, TC_FWD_STAGES = 4;
-constexpr int TC_BWD_BN = 128, TC_BWD_STAGES = 3;
+constexpr int TC_BWD_BN = 128, TC_BWD_STAGES = 4, TC_BWD_EPI_WARPS = 8;
 constexpr int TC_RD_STAGES = 4;
 
 static inline int tc_splits(long long tiles, long long k_total, int min_k) {
@@ -376,8 +651,13 @@ static inline int tc_forward_splits(int N, int V, int Ke) {
 static inline int tc_rowdot_splits(int N, int V, int Ke) {
   return tc_splits((long long)ceil_div(N, TC_BM) * ceil_div(Ke, TC_RDOT_BN), V, 1024);
 }
+// partial-sum arrays written by the backward epilogue: one per (voxel tile, column part)
+static inline int tc_bwd_col_parts(int V) { return (int)ceil_div(V, TC_BWD_BN) * (TC_BWD_EPI_WARPS / 4); }
 static inline int tc_kps(int k_total, int splits) {
   return (int)(round_up(ceil_div(k_total, splits), TC_BK));
+}
+static inline unsigned tc_grid(const TcContext& tc, long long total) {
+  return (unsigned)(total < tc.num_sms ? total : tc.num_sms);
 }
 
 // Y_ext[z] (V x Ke) = P[cells of split z]^T S_ext[...]
@@ -386,12 +666,12 @@ static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, const __nv_b
   CUtensorMap ma, mb;
   if (tc_make_map(tc, &ma, P, V, N, ld, 64, 64, err, n)) return -2;      // A: MN-major (voxels contiguous), rows = cells
   if (tc_make_map(tc, &mb, Sx, Ke, N, Ke, 64, 64, err, n)) return -2;    // B: MN-major (genes contiguous), rows = cells
-  auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 1, TcEpiStore>;
+  auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
   const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
-  TcEpiStore epi{out, Ke, (size_t)V * Ke, V, Ke};
-  dim3 grid((unsigned)ceil_div(Ke, TC_FWD_BN), (unsigned)ceil_div(V, TC_BM), splits);
-  kern<<<grid, TC_THREADS, smem, s>>>(ma, mb, N, tc_kps(N, splits), epi);
+  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
+  const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, N, tc_kps(N, splits), tm, tn, splits, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
 
@@ -401,27 +681,28 @@ static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, const __nv_bf
   CUtensorMap ma, mb;
   if (tc_make_map(tc, &ma, P, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
   if (tc_make_map(tc, &mb, dYb, Ke, V, Ke, 64, 64, err, n)) return -2;   // B: MN-major (genes contiguous), rows = voxels
-  auto kern = k_gemm_tc<true, false, TC_RDOT_BN, TC_RD_STAGES, 1, TcEpiRowDot>;
+  auto kern = k_gemm_tc<true, false, TC_RDOT_BN, TC_RD_STAGES, 4, TcEpiRowDot>;
   const int smem = TC_RD_STAGES * (TC_BM + TC_RDOT_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
-  TcEpiRowDot epi{Sxb, Ke, rpart, N, 0.f};
-  dim3 grid((unsigned)ceil_div(Ke, TC_RDOT_BN), (unsigned)ceil_div(N, TC_BM), splits);
-  kern<<<grid, TC_THREADS, smem, s>>>(ma, mb, V, tc_kps(V, splits), epi);
+  TcEpiRowDot epi{Sxb, Ke, rpart, N};
+  const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, V, tc_kps(V, splits), tm, tn, splits, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
-// dP = S_ext dY_ext^T fused with the softmax-Jacobian and Adam
+// dP = S_ext dY_ext^T fused with the softmax-Jacobian, Adam, and next iteration's P
 static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, const __nv_bfloat16* dYb, const TcAdamArgs& a,
                               int N, int V, int Ke, cudaStream_t s, char* err, size_t n) {
   CUtensorMap ma, mb;
   if (tc_make_map(tc, &ma, Sxb, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
   if (tc_make_map(tc, &mb, dYb, Ke, V, Ke, 64, TC_BWD_BN, err, n)) return -2; // B: K-major, rows = voxels
-  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, 2, TcEpiAdam>;
-  const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + 1024;
+  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
+  static_assert(TcEpiAdam::kStagingBytes == TC_BWD_EPI_WARPS * TcEpiAdam::kWarpBytes, "staging sized for the epilogue warps");
+  const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiAdam epi{a, N};
-  dim3 grid((unsigned)ceil_div(V, TC_BWD_BN), (unsigned)ceil_div(N, TC_BM), 1);
-  kern<<<grid, TC_THREADS, smem, s>>>(ma, mb, Ke, Ke, epi);
+  const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(V, TC_BWD_BN);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, Ke, Ke, tm, tn, 1, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 

@@ -84,6 +84,14 @@ struct tgb200_mapper {
   DevBuf<float> d, dsrc;
   DevBuf<RowStat> stats;
   DevBuf<float> rowaux, rdot, rpart;
+  DevBuf<float4> rowc;          // (lse, r, h, 0) per row for the tensor-core backward epilogue
+  // tensor-core path: row normalisation carried across iterations (see k_row_norm)
+  DevBuf<__nv_bfloat16> Sxs;    // N x Ke  bf16(S_ext / zt): forward B operand
+  DevBuf<float> lse0, lse1, inv_zt, zpart, pxpart, l1part, l2part;
+  float* lseA = nullptr;        // offset the current Pb was produced with
+  float* lseT = nullptr;        // exact log-sum-exp of the current rows
+  int z_parts = 0;
+  int p_state = 0;              // 0: Pb invalid, 1: fresh from the row pass (normalised), 2: written by backward
   int r_parts = 0, rd_splits = 1;
   // forward / loss
   int fwd_splits = 1;
@@ -176,7 +184,15 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   int st = TGB200_OK;
   auto A = [&](int s) { if (st == TGB200_OK) st = s; };
   A(h->M.alloc(nv)); A(h->m.alloc(nv)); A(h->v.alloc(nv));
-  if (h->bf16) { A(h->Pb.alloc(nv)); A(h->Sxb.alloc((size_t)h->N * h->Ke)); A(h->dYb.alloc(vk)); }
+  if (h->bf16) {
+    h->z_parts = tc_bwd_col_parts(h->V);
+    A(h->Sxs.alloc((size_t)h->N * h->Ke)); A(h->lse0.alloc(h->N)); A(h->lse1.alloc(h->N)); A(h->inv_zt.alloc(h->N));
+    A(h->zpart.alloc((size_t)h->z_parts * h->N));
+    if (cfg->lambda_r != 0.f) A(h->pxpart.alloc((size_t)h->z_parts * h->N));
+    if (cfg->lambda_l1 != 0.f || cfg->lambda_l2 != 0.f) { A(h->l1part.alloc((size_t)h->z_parts * h->N)); A(h->l2part.alloc((size_t)h->z_parts * h->N)); }
+    h->lseA = h->lse0.p; h->lseT = h->lse1.p;
+  }
+  if (h->bf16) { A(h->rowc.alloc(h->N)); A(h->Pb.alloc(nv)); A(h->Sxb.alloc((size_t)h->N * h->Ke)); A(h->dYb.alloc(vk)); }
   else A(h->Pf.alloc(nv));
   A(h->Sx.alloc((size_t)h->N * h->Ke));
   A(h->G.alloc(vk));
@@ -377,6 +393,7 @@ static int reset_optimizer(tgb200_mapper* h, cudaStream_t s) {
   h->step = 0;
   h->hist_len = 0;
   h->in_step = false;
+  h->p_state = 0;
   return TGB200_OK;
 }
 
@@ -458,12 +475,26 @@ static int check_ready(tgb200_mapper* h) {
 // forward: P, row statistics, Y_ext partial sums over this handle's cells
 static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
   float* rowaux = needs_rowaux(h->cfg) ? h->rowaux.p : nullptr;
-  if (h->bf16) CKS(launch_softmax_rows<__nv_bfloat16>(h, s, h->Pb.p, want_entropy, rowaux));
-  else CKS(launch_softmax_rows<float>(h, s, h->Pf.p, want_entropy, rowaux));
+  if (h->bf16) {
+    // The row pass runs only when P is not already resident (first iteration / after a state load):
+    // in steady state the previous backward epilogue has written P and its row sums.
+    if (h->p_state == 0) {
+      CKS(launch_softmax_rows<__nv_bfloat16>(h, s, h->Pb.p, 1, rowaux));
+      h->p_state = 1;
+    }
+    k_row_norm<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->N, h->p_state == 1 ? 1 : 0, h->zpart.p, h->pxpart.p, h->l1part.p,
+                                                            h->l2part.p, h->z_parts, h->lseA, h->lseT, h->inv_zt.p, h->stats.p, rowaux);
+    LAUNCH_CHECK("row_norm");
+    const long long nq = (long long)h->N * (h->Ke / 4);
+    k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->Sx.p, h->inv_zt.p, h->N, h->Ke, h->Sxs.p);
+    LAUNCH_CHECK("scale_rows");
+  } else {
+    CKS(launch_softmax_rows<float>(h, s, h->Pf.p, want_entropy, rowaux));
+  }
   const size_t vk = (size_t)h->V * h->Ke;
   float* out = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
   if (h->bf16) {
-    CKS(tc_forward(h->tc, h->Pb.p, h->Sxb.p, out, h->N, h->V, h->Ke, h->ld, h->fwd_splits, s, g_err, sizeof(g_err)));
+    CKS(tc_forward(h->tc, h->Pb.p, h->Sxs.p, out, h->N, h->V, h->Ke, h->ld, h->fwd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_fwd");
   } else {
     GemmArgs g;
@@ -560,6 +591,7 @@ static AdamScalars adam_scalars(const tgb200_config& c, int64_t t, float lr) {
   a.one_minus_beta1 = (float)(1.0 - b1); a.one_minus_beta2 = (float)(1.0 - b2);
   a.step_size = (float)((double)lr / bc1);
   a.bc2_sqrt = (float)std::sqrt(bc2);
+  a.inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
   a.eps = c.adam_eps;
   return a;
 }
@@ -588,12 +620,21 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     k_gemm_simt<true, false, EpiRowDot><<<grid, SG_THREADS, 0, s>>>(g, epi);
     LAUNCH_CHECK("simt_gemm_rowdot");
   }
-  k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p);
+  if (h->bf16) {
+    k_rowdot_finalize_tc<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->lseT, h->inv_zt.p, h->stats.p,
+                                                                        h->rdot.p, h->rowc.p);
+  } else {
+    k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p, h->stats.p, nullptr);
+  }
   LAUNCH_CHECK("rowdot_finalize");
   if (h->bf16) {
-    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, h->stats.p, h->rdot.p, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, reinterpret_cast<const RowConst*>(h->rowc.p), h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
+                  h->Pb.p, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p};
     CKS(tc_backward(h->tc, h->Sxb.p, h->dYb.p, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_bwd_adam");
+    // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
+    float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
+    h->p_state = 2;
   } else {
     GemmArgs g;
     g.A = h->Sx.p; g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
@@ -673,7 +714,7 @@ extern "C" int tgb200_set_state(tgb200_mapper* h, const float* M, const float* m
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
   const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
-  if (M) { CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; }
+  if (M) { CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; h->p_state = 0; }
   if (m) CK(cudaMemcpy2DAsync(h->m.p, pitch, m, w, w, h->N, cudaMemcpyDefault, s));
   if (v) CK(cudaMemcpy2DAsync(h->v.p, pitch, v, w, w, h->N, cudaMemcpyDefault, s));
   h->step = step;

@@ -96,3 +96,22 @@ def test_tc_determinism():
     a, _ = Mapper(**kw).train(8, print_each=None)
     b, _ = Mapper(**kw).train(8, print_each=None)
     assert np.array_equal(a, b)
+
+
+def test_tc_resume_reinitialises_row_normalisation():
+    """A state load drops the resident P (written by the backward epilogue) and re-runs the row pass:
+    6 steps == 3 steps + checkpoint/restore + 3 steps up to bf16 rounding."""
+    from tangram_b200 import Mapper
+    inp = synthetic_inputs(1500, 500, 200, seed=3)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, lambda_r=1e-3, random_state=4, precision="bf16",
+              device="cuda:0")
+    a, ha = Mapper(**kw).train(6, print_each=None)
+    m1 = Mapper(**kw)
+    m1.train(3, print_each=None)
+    st = m1.state()
+    m2 = Mapper(**kw)
+    m2.load_state(*st)
+    b, hb = m2.train(3, print_each=None)
+    assert rel_fro(b, a) < 5e-3
+    assert abs(float(hb["total_loss"][-1]) - float(ha["total_loss"][-1])) < 1e-4
+    assert abs(hb["entropy_reg"][-1] - ha["entropy_reg"][-1]) < 1e-3 * abs(ha["entropy_reg"][-1])
