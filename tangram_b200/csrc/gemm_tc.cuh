@@ -61,12 +61,39 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // L2 policy: operand tiles are re-read by many CTAs -> evict_last (CUTLASS TMA::CacheHintSm90::EVICT_LAST)
+constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kPolicyEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(kPolicyEvictLast) : "memory");
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -130,12 +157,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
 template <bool KMAJOR, int ROWS>
 struct OperandTile {
   static constexpr int kBytes = ROWS * TC_BK * 2;
-  static __device__ __forceinline__ void load(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int mn0, int k0) {
+  static __device__ __forceinline__ void load(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int mn0, int k0, uint64_t policy) {
     if (KMAJOR) {
-      tma_load_2d(map, bar, dst, k0, mn0);                       // box {64 k, ROWS mn}
+      tma_load_2d(map, bar, dst, k0, mn0, policy);               // box {64 k, ROWS mn}
     } else {
 #pragma unroll
-      for (int b = 0; b < ROWS / 64; ++b) tma_load_2d(map, bar, dst + b * 8192, mn0 + b * 64, k0);  // box {64 mn, 64 k}
+      for (int b = 0; b < ROWS / 64; ++b) tma_load_2d(map, bar, dst + b * 8192, mn0 + b * 64, k0, policy);  // box {64 mn, 64 k}
     }
   }
   static __device__ __forceinline__ uint64_t desc(uint32_t saddr, int k_step /* 0..3 */) {
@@ -143,6 +170,17 @@ struct OperandTile {
     return make_smem_desc(saddr + k_step * (TC_UMMA_K * 128), 8192, 1024);
   }
 };
+
+// Optional phase timing of the backward epilogue (build with -DTGB_EPI_TIMING): lane 0 of every epilogue
+// warp accumulates clock64() deltas per phase into g_epi_timing[phase] (atomicAdd at kernel end).
+#ifdef TGB_EPI_TIMING
+__device__ unsigned long long g_epi_timing[8];
+#define TGB_T0() long long t__ = clock64()
+#define TGB_TICK(acc) do { long long n__ = clock64(); acc += n__ - t__; t__ = n__; } while (0)
+#else
+#define TGB_T0() do {} while (0)
+#define TGB_TICK(acc) do {} while (0)
+#endif
 
 // ---- epilogues ------------------------------------------------------------------------------
 // Each epilogue warp owns TMEM lanes [32q, 32q+32) = output rows m0+32q.. of the tile.
@@ -172,15 +210,22 @@ struct TileCoord {
   int split;         // k-split index
 };
 
+// What the kernel hands to an epilogue that stages global data through shared memory with TMA.
+struct EpiCtx {
+  const CUtensorMap* map[3];   // state arrays (M, m, v) as fp32 2D tensors, box 32 x 32, 128B swizzle
+  uint32_t staging;            // shared-memory staging area (1024-byte aligned)
+  uint32_t bars;               // 8 mbarriers: [group 0..3][buffer 0..1]
+  uint32_t use0, use1;         // completed uses of this thread's two staging buffers (mbarrier parity)
+};
+
 struct TcEpiStore {
   float* C; int ldc; size_t split_stride; int M;
   static constexpr int kStagingBytes = 0;
   template <int BN, int NW>
-  __device__ __forceinline__ void prefetch_next(const TileCoord&, int, int, int) {}
+  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, EpiCtx&) const {}
+  __device__ __forceinline__ void finish(int, int, int) const {}
   template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, uint32_t) {}
-  template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, uint32_t) {
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, EpiCtx&) const {
     static_assert(NW == 4, "one warp per TMEM lane quarter");
     const int row = t.m0 + q * 32 + lane;
 #pragma unroll 1
@@ -201,11 +246,10 @@ struct TcEpiRowDot {
   const __nv_bfloat16* S; int lds; float* rpart; int M;
   static constexpr int kStagingBytes = 0;
   template <int BN, int NW>
-  __device__ __forceinline__ void prefetch_next(const TileCoord&, int, int, int) {}
+  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, EpiCtx&) const {}
+  __device__ __forceinline__ void finish(int, int, int) const {}
   template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, uint32_t) {}
-  template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, uint32_t) {
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, EpiCtx&) const {
     static_assert(NW == 4, "one warp per TMEM lane quarter");
     const int row = t.m0 + q * 32 + lane;
     float acc = 0.f;
@@ -250,39 +294,35 @@ struct TcAdamArgs {
   float* l2part;
 };
 
-// The three N x V state arrays are the HBM-bound part of the whole iteration (24 B/element), so
-// the epilogue is built around bytes in flight, not instructions: every warp stages its own
-// 32-row x 16-column sub-tiles of M, m, v into shared memory with cp.async (16 B per lane, one warp
-// instruction = 8 rows x 64 contiguous bytes), two sub-tiles deep (12 KB in flight per warp, 96 KB
-// per CTA), updates them in shared memory with one thread per row (matching the TMEM accumulator
-// layout; 16-byte chunks XOR-swizzled by row so both access patterns are bank-conflict free) and
-// streams them back with coalesced 128-bit stores.  All synchronisation is warp-local
-// (cp.async.wait_group + __syncwarp).
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(kPolicyEvictFirst) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void st_stream_hint(float4* p, const float4& v) {
-  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
-               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(kPolicyEvictFirst) : "memory");
-}
-
+// The three N x V state arrays are the HBM-bound part of the whole iteration (24 B/element), so the
+// epilogue is built around bytes in flight and full-line transactions: the two warps that share a
+// TMEM lane quarter form a group that stages 32-row x 32-column sub-tiles of M, m, v through shared
+// memory with TMA -- bulk tensor loads (128 contiguous bytes per row, 128B-swizzled so that one
+// thread per row reads and writes conflict-free) two sub-tiles deep, in-place update with one thread
+// per row (matching the TMEM accumulator layout), bulk tensor stores back.  No LSU traffic for the
+// state at all; the only per-thread global access is the bf16 P row for the next forward pass.
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// Blackwell packed-fp32 arithmetic (fma/add/mul .f32x2): two elements per instruction on the FMA pipe.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 struct TcEpiAdam {
   TcAdamArgs p; int M;
-  static constexpr int CW = 16;                            // columns per staged sub-tile
-  static constexpr int kArrayBytes = 32 * CW * 4;          // 32 rows x 16 floats = 2 KB
+  static constexpr int CW = 16;                            // columns per warp per staged sub-tile
+  static constexpr int SW = 32;                            // staged sub-tile width (two warps)
+  static constexpr int kArrayBytes = 32 * SW * 4;          // 32 rows x 128 B = 4 KB
   static constexpr int kBufBytes = 3 * kArrayBytes;        // M, m, v
-  static constexpr int kWarpBytes = 2 * kBufBytes;         // double buffered: 12 KB per warp
-  static constexpr int kStagingBytes = 8 * kWarpBytes;     // 8 epilogue warps
-  // 64-byte rows, 16-byte chunks XOR-swizzled so that both "thread = row" and "8 rows x 4 chunks per
-  // warp instruction" are bank-conflict free.
-  static __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+  static constexpr int kGroupBytes = 2 * kBufBytes;        // double buffered: 24 KB per group
+  static constexpr int kStagingBytes = 4 * kGroupBytes;    // 4 lane quarters
+  // TMA SWIZZLE_128B: 16-byte chunk jj of row r lives at chunk position jj ^ (r & 7)
+  static __device__ __forceinline__ uint32_t swz(int r, int jj) { return (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4)); }
 
   // bf16-mode arithmetic: approximate MUFU ops (ex2, sqrt, rcp), ~2 ulp -- far below bf16 operand noise
   __device__ __forceinline__ float one(float x, float dp, float& m, float& v, const RowConst& rc, float lse_l2e) const {
@@ -305,82 +345,94 @@ struct TcEpiAdam {
     if (p.l1part) { l1s += fabsf(xn); l2s = fmaf(xn, xn, l2s); }
     return pt;
   }
-  // global -> shared (coalesced): lane handles rows sub + 8 i, 16-byte chunk j
-  __device__ __forceinline__ void prefetch(uint32_t buf, int row0, int col0, int lane) const {
-    const int sub = lane >> 2, j = lane & 3;
-    const int col = col0 + 4 * j;
-    if (col < p.ld) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rl = sub + 8 * i;
-        const int row = row0 + rl;
-        if (row < M) {
-          const size_t o = (size_t)row * p.ld + col;
-          const uint32_t d = buf + swz(rl, j);
-          cp_async16(d, p.Mp + o);
-          cp_async16(d + kArrayBytes, p.mp + o);
-          cp_async16(d + 2 * kArrayBytes, p.vp + o);
-        }
-      }
-    }
+  // leader lane of a group: three bulk tensor loads of sub-tile `c` into staging buffer `b`
+  __device__ __forceinline__ void issue_loads(const EpiCtx& cx, int g, int b, int row0, int col) const {
+    const uint32_t bar = cx.bars + (uint32_t)(g * 2 + b) * 8u;
+    const uint32_t dst = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
+    mbar_expect_tx_u32(bar, kBufBytes);
+    tma_load_2d_u32(cx.map[0], bar, dst, col, row0, kPolicyEvictFirst);
+    tma_load_2d_u32(cx.map[1], bar, dst + kArrayBytes, col, row0, kPolicyEvictFirst);
+    tma_load_2d_u32(cx.map[2], bar, dst + 2 * kArrayBytes, col, row0, kPolicyEvictFirst);
   }
-  __device__ __forceinline__ void writeback(uint32_t buf, int row0, int col0, int lane) const {
-    const int sub = lane >> 2, j = lane & 3;
-    const int col = col0 + 4 * j;
-    if (col < p.ld) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rl = sub + 8 * i;
-        const int row = row0 + rl;
-        if (row < M) {
-          const size_t o = (size_t)row * p.ld + col;
-          const uint32_t sp = buf + swz(rl, j);
-          st_stream_hint(reinterpret_cast<float4*>(p.Mp + o), lds128(sp));
-          st_stream_hint(reinterpret_cast<float4*>(p.mp + o), lds128(sp + kArrayBytes));
-          st_stream_hint(reinterpret_cast<float4*>(p.vp + o), lds128(sp + 2 * kArrayBytes));
-        }
-      }
-    }
-  }
-  // DRAM -> L2 prefetch of the NEXT tile's M, m, v rows (this warp's 32 rows x COLS columns), one
-  // bulk prefetch per 256-byte row segment.  The cp.async loads of the next tile then hit L2, so the
-  // 96 KB of shared-memory staging is enough bytes in flight to run at HBM rate.
-  template <int BN, int NW>
-  __device__ __forceinline__ void prefetch_next(const TileCoord& t, int q, int ew, int lane) {
-    constexpr int COLS = BN / (NW / 4);
-    const int row = t.m0 + q * 32 + lane;
-    const int col = t.n0 + (ew >> 2) * COLS;
-    if (row < M && col < p.ld) {
-      const int ncol = min(COLS, p.ld - col);
-      const size_t o = (size_t)row * p.ld + col;
-      const uint32_t bytes = (uint32_t)ncol * 4u;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Mp + o), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.mp + o), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.vp + o), "r"(bytes) : "memory");
-    }
+  __device__ __forceinline__ void issue_stores(const EpiCtx& cx, int g, int b, int row0, int col) const {
+    const uint32_t src = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
+    tma_store_2d(cx.map[0], src, col, row0, kPolicyEvictFirst);
+    tma_store_2d(cx.map[1], src + kArrayBytes, col, row0, kPolicyEvictFirst);
+    tma_store_2d(cx.map[2], src + 2 * kArrayBytes, col, row0, kPolicyEvictFirst);
+    bulk_commit();
   }
   // Issued before the wait on the accumulator: the first two sub-tiles are already in flight when the
-  // MMAs of this tile retire.
+  // MMAs of this tile retire.  (The leader drained its bulk stores at the end of the previous tile.)
   template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, uint32_t staging) {
-    constexpr int COLS = BN / (NW / 4);
-    const uint32_t wbuf = staging + ew * kWarpBytes;
-    const int row0 = t.m0 + q * 32;
-    const int cbase = t.n0 + (ew >> 2) * COLS;
-    prefetch(wbuf, row0, cbase, lane);
-    cp_async_commit();
-    prefetch(wbuf + kBufBytes, row0, cbase + CW, lane);
-    cp_async_commit();
+  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx& cx) const {
+    static_assert(NW == 8, "two warps per TMEM lane quarter");
+    if (ew < 4 && lane == 0) {
+      issue_loads(cx, q, 0, t.m0 + q * 32, t.n0);
+      issue_loads(cx, q, 1, t.m0 + q * 32, t.n0 + SW);
+    }
+  }
+  __device__ __forceinline__ void finish(int ew, int lane, int) const {
+    if (ew < 4 && lane == 0) bulk_wait0();     // all bulk stores of this CTA have landed before exit
+  }
+  // Two adjacent elements of one row through the whole update (default loss: no entropy / L1 / L2):
+  // 13 packed FMA-pipe instructions + 8 MUFU for the pair.
+  struct PairConsts { f32x2 l2e, nlse, nr, omb1, omb2, b2, ibc, eps, nstep; };
+  __device__ __forceinline__ void pair(float& x0, float& x1, float dp0, float dp1, float& m0, float& m1, float& v0,
+                                       float& v1, const PairConsts& k, float& p0, float& p1) const {
+    f32x2 x = pk2(x0, x1), m = pk2(m0, m1), v = pk2(v0, v1);
+    f32x2 t = fma2(x, k.l2e, k.nlse);
+    float e0, e1;
+    upk2(t, e0, e1);
+    f32x2 g = mul2(add2(pk2(dp0, dp1), k.nr), pk2(fast_ex2(e0), fast_ex2(e1)));
+    m = fma2(add2(g, m ^ 0x8000000080000000ull), k.omb1, m);          // m + (g - m)(1-b1)
+    v = fma2(mul2(k.omb2, g), g, mul2(v, k.b2));
+    float s0, s1;
+    upk2(v, s0, s1);
+    f32x2 den = fma2(pk2(fast_sqrt(s0), fast_sqrt(s1)), k.ibc, k.eps);
+    float d0, d1;
+    upk2(den, d0, d1);
+    x = fma2(mul2(k.nstep, m), pk2(fast_rcp(d0), fast_rcp(d1)), x);
+    t = fma2(x, k.l2e, k.nlse);
+    upk2(t, e0, e1);
+    p0 = fast_ex2(e0); p1 = fast_ex2(e1);
+    upk2(x, x0, x1); upk2(m, m0, m1); upk2(v, v0, v1);
+  }
+  __device__ __forceinline__ void update_chunk_fast(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[16],
+                                                    const RowConst& rc, float lse_l2e, float& zs) const {
+    PairConsts k;
+    k.l2e = pk2(1.4426950408889634f, 1.4426950408889634f); k.nlse = pk2(-lse_l2e, -lse_l2e); k.nr = pk2(-rc.r, -rc.r);
+    k.omb1 = pk2(p.a.one_minus_beta1, p.a.one_minus_beta1); k.omb2 = pk2(p.a.one_minus_beta2, p.a.one_minus_beta2);
+    k.b2 = pk2(p.a.beta2, p.a.beta2); k.ibc = pk2(p.a.inv_bc2_sqrt, p.a.inv_bc2_sqrt); k.eps = pk2(p.a.eps, p.a.eps);
+    k.nstep = pk2(-p.a.step_size, -p.a.step_size);
+    uint32_t pkd[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t sp = buf + swz(lane, jbase + j);
+      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
+      float p0, p1, p2, p3;
+      pair(x.x, x.y, acc[4 * j + 0], acc[4 * j + 1], m.x, m.y, v.x, v.y, k, p0, p1);
+      pair(x.z, x.w, acc[4 * j + 2], acc[4 * j + 3], m.z, m.w, v.z, v.w, k, p2, p3);
+      zs += (p0 + p1) + (p2 + p3);
+      sts128(sp, x);
+      sts128(sp + kArrayBytes, m);
+      sts128(sp + 2 * kArrayBytes, v);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+      pkd[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
+      pkd[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
+    dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
+    dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
   }
   // one 16-column sub-tile, thread = row.  GUARD=false: all 16 columns are real voxels.
   template <bool GUARD>
-  __device__ __forceinline__ void update_chunk(uint32_t buf, int lane, int row, int col0, const float (&acc)[16],
+  __device__ __forceinline__ void update_chunk(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[16],
                                                const RowConst& rc, float lse_l2e, float& zs, float& pxs, float& l1s,
                                                float& l2s) const {
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t sp = buf + swz(lane, j);
+      const uint32_t sp = buf + swz(lane, jbase + j);
       float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
       const int col = col0 + 4 * j;
       float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
@@ -400,43 +452,53 @@ struct TcEpiAdam {
     dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
-  // ew = epilogue warp index (0..NW-1); TMEM lane quarter q; this warp owns columns [part*BN/parts, ...)
+  // ew = epilogue warp index; group = TMEM lane quarter q; part = ew / 4 picks the 16-column half of every
+  // 32-column staged sub-tile.
   template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, uint32_t staging) {
-    constexpr int PARTS = NW / 4;
-    constexpr int COLS = BN / PARTS;
-    constexpr int NCHUNK = COLS / CW;
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx& cx) const {
+    static_assert(NW == 8, "two warps per TMEM lane quarter");
+    constexpr int NCHUNK = BN / SW;
     static_assert(NCHUNK >= 2, "prologue prefetches two sub-tiles");
     const int part = ew >> 2;
-    const uint32_t wbuf = staging + ew * kWarpBytes;
+    const bool leader = (part == 0) && (lane == 0);
     const int row0 = t.m0 + q * 32;
     const int row = row0 + lane;
-    const int cbase = t.n0 + part * COLS;
     RowConst rc = {0.f, 0.f, 0.f, 0.f};
     if (row < M) rc = p.rowc[row];
     const float lse_l2e = rc.lse * 1.4426950408889634f;
     float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
+    const bool plain = p.lam_r == 0.f && p.lam_l1 == 0.f && p.lam_l2 == 0.f;   // default loss: packed fast path
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c) {
-      const uint32_t buf = wbuf + (c & 1) * kBufBytes;
-      const int col0 = cbase + c * CW;
-      if (c + 1 < NCHUNK) cp_async_wait<1>(); else cp_async_wait<0>();
-      __syncwarp();
+      const int b = c & 1;
+      const uint32_t buf = cx.staging + (uint32_t)(q * kGroupBytes + b * kBufBytes);
+      const int colg = t.n0 + c * SW;             // first column of the staged sub-tile
+      const int col0 = colg + part * CW;          // first column this warp updates
+      mbar_wait_u32(cx.bars + (uint32_t)(q * 2 + b) * 8u, (b ? cx.use1 : cx.use0) & 1u);
+      if (b) cx.use1++; else cx.use0++;
       float acc[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * COLS + c * CW), acc);
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
       if (row < M && col0 < p.ld) {
-        if (col0 + CW <= p.V) update_chunk<false>(buf, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
-        else update_chunk<true>(buf, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+        if (col0 + CW <= p.V) {
+          if (plain) update_chunk_fast(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs);
+          else update_chunk<false>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+        } else {
+          update_chunk<true>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+        }
       }
-      __syncwarp();
-      writeback(buf, row0, col0, lane);
-      __syncwarp();
-      if (c + 2 < NCHUNK) prefetch(buf, row0, cbase + (c + 2) * CW, lane);
-      cp_async_commit();
+      fence_proxy_async();                        // generic-proxy writes -> visible to the bulk store
+      named_bar_sync(1 + q, 64);                  // both warps of the group are done with this buffer
+      if (leader) {
+        issue_stores(cx, q, b, row0, colg);
+        if (c + 2 < NCHUNK) {
+          bulk_wait_read0();                      // the store has read the buffer: refill it
+          issue_loads(cx, q, b, row0, colg + 2 * SW);
+        }
+      }
     }
-    cp_async_wait<0>();
+    if (leader) bulk_wait_read0();                // buffers reusable by the next tile's prologue
     if (row < M) {
-      const size_t o = ((size_t)t.tile_n * PARTS + part) * M + row;
+      const size_t o = ((size_t)t.tile_n * 2 + part) * M + row;
       p.zpart[o] = zs;
       if (p.pxpart) p.pxpart[o] = pxs;
       if (p.l1part) { p.l1part[o] = l1s; p.l2part[o] = l2s; }
@@ -450,7 +512,10 @@ struct TcEpiAdam {
 template <bool A_KMAJOR, bool B_KMAJOR, int BN, int STAGES, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, Epi epi) {
+          const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
+          const __grid_constant__ CUtensorMap map_e2,
+          int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, uint64_t policy_a, uint64_t policy_b,
+          const Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
   using TileB = OperandTile<B_KMAJOR, BN>;
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
@@ -464,6 +529,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t epi_bar[8];      // epilogue staging: [lane quarter][buffer]
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -476,6 +542,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) mbar_init(&epi_bar[b], 1);
+    if (Epi::kStagingBytes > 0) { tma_prefetch_desc(&map_e0); tma_prefetch_desc(&map_e1); tma_prefetch_desc(&map_e2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -503,8 +572,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           uint8_t* sb = sa + TileA::kBytes;
           mbar_expect_tx(&full_bar[s], kStageBytes);
           const int k0 = k_begin + kb * TC_BK;
-          TileA::load(&map_a, &full_bar[s], sa, m0, k0);
-          TileB::load(&map_b, &full_bar[s], sb, n0, k0);
+          TileA::load(&map_a, &full_bar[s], sa, m0, k0, policy_a);
+          TileB::load(&map_b, &full_bar[s], sb, n0, k0, policy_b);
         }
       }
     }
@@ -541,7 +610,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     // ===== epilogue warps: TMEM -> registers -> fused epilogue =====
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int ew = warp - 2;
-    const uint32_t staging = smem_u32(smem + STAGES * kStageBytes);
+    EpiCtx cx;
+    cx.map[0] = &map_e0; cx.map[1] = &map_e1; cx.map[2] = &map_e2;
+    cx.staging = smem_u32(smem + STAGES * kStageBytes);
+    cx.bars = smem_u32(&epi_bar[0]);
+    cx.use0 = 0; cx.use1 = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       TileCoord t;
@@ -551,26 +624,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       t.m0 = ((w / tiles_n) % tiles_m) * TC_BM;
       t.split = w / (tiles_n * tiles_m);
       const int b = it & 1;
-      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, staging);
-      {
-        const int wn = w + (int)gridDim.x;
-        if (wn < total) {
-          TileCoord tn;
-          tn.tile_n = wn % tiles_n;
-          tn.tiles_n = tiles_n;
-          tn.n0 = tn.tile_n * BN;
-          tn.m0 = ((wn / tiles_n) % tiles_m) * TC_BM;
-          tn.split = wn / (tiles_n * tiles_m);
-          epi.template prefetch_next<BN, EPI_WARPS>(tn, q, ew, lane);
-        }
-      }
+#ifndef TGB_SKIP_EPI
+      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
+#endif
       mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
-      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, staging);
+#ifndef TGB_SKIP_EPI
+      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, cx);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[b]);
     }
+    epi.finish(ew, lane, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -615,6 +681,23 @@ static inline int tc_make_map(TcContext& tc, CUtensorMap* map, const void* base,
   if (r != CUDA_SUCCESS) {
     snprintf(err, n, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu ld=%llu box=%ux%u", (int)r,
              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld, box_inner, box_outer);
+    return -2;
+  }
+  return 0;
+}
+
+static inline int tc_make_map_f32(TcContext& tc, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows,
+                                  uint64_t ld, uint32_t box_inner, uint32_t box_outer, char* err, size_t n) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = tc.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, n, "cuTensorMapEncodeTiled(f32) failed (%d) cols=%llu rows=%llu ld=%llu", (int)r,
+             (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
     return -2;
   }
   return 0;
@@ -671,7 +754,7 @@ static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, const __nv_b
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, N, tc_kps(N, splits), tm, tn, splits, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, ma, ma, ma, N, tc_kps(N, splits), tm, tn, splits, kPolicyEvictNormal, kPolicyEvictNormal, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
 
@@ -686,7 +769,7 @@ static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, const __nv_bf
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiRowDot epi{Sxb, Ke, rpart, N};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, V, tc_kps(V, splits), tm, tn, splits, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, ma, ma, ma, V, tc_kps(V, splits), tm, tn, splits, kPolicyEvictNormal, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
@@ -696,13 +779,17 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, const __n
   CUtensorMap ma, mb;
   if (tc_make_map(tc, &ma, Sxb, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
   if (tc_make_map(tc, &mb, dYb, Ke, V, Ke, 64, TC_BWD_BN, err, n)) return -2; // B: K-major, rows = voxels
+  // state arrays as fp32 2D tensors [N][V] (pitch ld): 32 x 32 boxes, 128B swizzle; stores clip at V / N
+  CUtensorMap me[3];
+  float* st[3] = {a.Mp, a.mp, a.vp};
+  for (int i = 0; i < 3; ++i)
+    if (tc_make_map_f32(tc, &me[i], st[i], V, N, a.ld, 32, 32, err, n)) return -2;
   auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
-  static_assert(TcEpiAdam::kStagingBytes == TC_BWD_EPI_WARPS * TcEpiAdam::kWarpBytes, "staging sized for the epilogue warps");
   const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiAdam epi{a, N};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(V, TC_BWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, Ke, Ke, tm, tn, 1, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, me[0], me[1], me[2], Ke, Ke, tm, tn, 1, kPolicyEvictNormal, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 

@@ -870,6 +870,15 @@ extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* ou
   return TGB200_OK;
 }
 
+#ifdef TGB_EPI_TIMING
+extern "C" __attribute__((visibility("default"))) int tgb200_debug_epi_timing(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 extern "C" int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   const double N = h->N, V = h->V, K = h->K, T = h->T;
