@@ -468,6 +468,10 @@ struct TcEpiAdam {
     const float lse_l2e = rc.lse * 1.4426950408889634f;
     float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
     const bool plain = p.lam_r == 0.f && p.lam_l1 == 0.f && p.lam_l2 == 0.f;   // default loss: packed fast path
+#ifdef TGB_EPI_TIMING
+    long long tw = 0, tc = 0, tb = 0, tp = 0;
+#endif
+    TGB_T0();
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c) {
       const int b = c & 1;
@@ -476,6 +480,7 @@ struct TcEpiAdam {
       const int col0 = colg + part * CW;          // first column this warp updates
       mbar_wait_u32(cx.bars + (uint32_t)(q * 2 + b) * 8u, (b ? cx.use1 : cx.use0) & 1u);
       if (b) cx.use1++; else cx.use0++;
+      TGB_TICK(tw);
       float acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
       if (row < M && col0 < p.ld) {
@@ -486,8 +491,10 @@ struct TcEpiAdam {
           update_chunk<true>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
         }
       }
+      TGB_TICK(tc);
       fence_proxy_async();                        // generic-proxy writes -> visible to the bulk store
       named_bar_sync(1 + q, 64);                  // both warps of the group are done with this buffer
+      TGB_TICK(tb);
       if (leader) {
         issue_stores(cx, q, b, row0, colg);
         if (c + 2 < NCHUNK) {
@@ -495,8 +502,17 @@ struct TcEpiAdam {
           issue_loads(cx, q, b, row0, colg + 2 * SW);
         }
       }
+      TGB_TICK(tp);
     }
     if (leader) bulk_wait_read0();                // buffers reusable by the next tile's prologue
+#ifdef TGB_EPI_TIMING
+    if (lane == 1) {
+      atomicAdd(&g_epi_timing[0], (unsigned long long)tw); atomicAdd(&g_epi_timing[1], (unsigned long long)tc);
+      atomicAdd(&g_epi_timing[2], (unsigned long long)tb); atomicAdd(&g_epi_timing[3], (unsigned long long)tp);
+      atomicAdd(&g_epi_timing[4], 1ull);
+    }
+    if (leader) { atomicAdd(&g_epi_timing[6], (unsigned long long)tp); atomicAdd(&g_epi_timing[7], 1ull); }
+#endif
     if (row < M) {
       const size_t o = ((size_t)t.tile_n * 2 + part) * M + row;
       p.zpart[o] = zs;
@@ -627,7 +643,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #ifndef TGB_SKIP_EPI
       epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
 #endif
+#ifdef TGB_EPI_TIMING
+      long long tq0 = clock64();
+#endif
       mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
+#ifdef TGB_EPI_TIMING
+      if (lane == 1 && Epi::kStagingBytes > 0) atomicAdd(&g_epi_timing[5], (unsigned long long)(clock64() - tq0));
+#endif
       tc_fence_after();
 #ifndef TGB_SKIP_EPI
       epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, cx);

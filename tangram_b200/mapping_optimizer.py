@@ -17,6 +17,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
+from .sharded import shard_rows, sharded_steps
 
 _HIST_KEYS = ["total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg"]
 _VAL_KEYS = ["val_total_loss", "val_gene_sim", "val_sp_sparsity_weighted_sim", "val_entropy"]
@@ -235,12 +236,20 @@ class Mapper:
             return
         import torch
         import torch.distributed as dist
-        buf = self._exchange_tensor()
-        stream = torch.cuda.current_stream(self._cfg.device).cuda_stream
-        for _ in range(n_steps):
-            _lib.check(self._lib.tgb200_step_begin(self._h, ctypes.c_void_p(stream)))
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._pg)      # the one exchange per step
-            _lib.check(self._lib.tgb200_step_end(self._h, lr, ctypes.c_void_p(stream)))
+        mapper, stream = self, ctypes.c_void_p(torch.cuda.current_stream(self._cfg.device).cuda_stream)
+
+        class _Eng:   # the engine protocol of tangram_b200.sharded over the C-ABI handle
+            def exchange_tensor(self):
+                return mapper._exchange_tensor()
+
+            def step_begin(self):
+                _lib.check(mapper._lib.tgb200_step_begin(mapper._h, stream))
+
+            def step_end(self, lr_):
+                _lib.check(mapper._lib.tgb200_step_end(mapper._h, lr_, stream))
+
+        sharded_steps(_Eng(), n_steps, lr,
+                      lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._pg))   # the one exchange per step
 
     def train(self, num_epochs, learning_rate=0.1, print_each=100, val_each=None):
         """mapping_optimizer.py:358-408.  Returns (softmax(M) as (N, V) f32 ndarray, history)."""
@@ -315,10 +324,3 @@ class Mapper:
         n = ctypes.c_int64()
         _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))
         return n.value
-
-
-def shard_rows(n_cells, rank, world):
-    """Contiguous cell-row block of `rank`: balanced to within one row."""
-    base, rem = divmod(n_cells, world)
-    r0 = rank * base + min(rank, rem)
-    return r0, r0 + base + (1 if rank < rem else 0)

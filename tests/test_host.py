@@ -1,0 +1,140 @@
+"""Host-side logic of the reference-shaped API (no GPU needed): AnnData stand-in, pp_adatas,
+cluster aggregation, sparse spatial weights, argument validation with the reference's messages."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+import tangram_b200 as tg
+from oracle.tangram_oracle import grid_graph, spatial_weights_from_graph
+from tangram_b200 import spatial_weights as sw
+
+
+def _mock_pair():
+    # same shape as the reference's mocks (tests/tangram_test.py:31-47)
+    ad_sc = tg.MiniAnnData(X=np.array([[0, 1, 1], [0, 1, 1]], dtype=np.float32),
+                           obs=pd.DataFrame(index=["cell_1", "cell_2"]),
+                           var=pd.DataFrame(index=["gene_a", "gene_b", "gene_d"]))
+    ad_sp = tg.MiniAnnData(X=np.array([[0, 1, 1, 1], [0, 1, 1, 1]], dtype=np.float32),
+                           obs=pd.DataFrame(index=["voxel_1", "voxel_2"]),
+                           var=pd.DataFrame(index=["gene_c", "gene_b", "gene_a", "gene_d"]))
+    return ad_sc, ad_sp
+
+
+def test_pp_adatas_populates_fields():
+    """tests/tangram_test.py:53-61."""
+    ad_sc, ad_sp = _mock_pair()
+    tg.pp_adatas(ad_sc, ad_sp)
+    for ad in (ad_sc, ad_sp):
+        assert "training_genes" in ad.uns and "overlap_genes" in ad.uns
+    assert sorted(ad_sc.uns["training_genes"]) == ["gene_b", "gene_d"]      # gene_a is all-zero in sc -> filtered
+    assert "rna_count_based_density" in ad_sp.obs.keys() and "uniform_density" in ad_sp.obs.keys()
+    assert np.isclose(ad_sp.obs["rna_count_based_density"].sum(), 1.0)
+    assert np.allclose(ad_sp.obs["uniform_density"], 0.5)
+
+
+def test_minianndata_indexing():
+    ad = tg.MiniAnnData(X=np.arange(12, dtype=np.float32).reshape(3, 4),
+                        obs=pd.DataFrame({"lab": list("aba")}, index=["c0", "c1", "c2"]),
+                        var=pd.DataFrame(index=["g0", "g1", "g2", "g3"]))
+    sub = ad[:, ["g2", "g0"]]
+    assert sub.shape == (3, 2) and np.array_equal(sub.X[:, 0], ad.X[:, 2])
+    rows = ad[np.asarray(ad.obs["lab"] == "a")]
+    assert rows.shape == (2, 4) and list(rows.obs_names) == ["c0", "c2"]
+    with pytest.raises(KeyError):
+        ad[:, ["nope"]]
+
+
+def test_cluster_expression_matches_reference_semantics():
+    """mapping_utils.py:103-139: sum (scale=True) or mean per label, cluster_density = label frequency."""
+    X = np.arange(20, dtype=np.float32).reshape(5, 4)
+    ad = tg.MiniAnnData(X=X, obs=pd.DataFrame({"lab": ["x", "y", "x", "x", "y"]}, index=[f"c{i}" for i in range(5)]),
+                        var=pd.DataFrame(index=list("abcd")))
+    agg = tg.adata_to_cluster_expression(ad, "lab", scale=True)
+    labs = list(agg.obs["lab"])
+    assert labs[0] == "x"                                                   # value_counts order: most frequent first
+    assert np.allclose(agg.X[labs.index("x")], X[[0, 2, 3]].sum(0))
+    assert np.allclose(agg.obs["cluster_density"], [0.6, 0.4])
+    mean = tg.adata_to_cluster_expression(ad, "lab", scale=False)
+    assert np.allclose(mean.X[labs.index("y")], X[[1, 4]].mean(0))
+    with pytest.raises(ValueError, match="Provided label must belong"):
+        tg.adata_to_cluster_expression(ad, "nope")
+
+
+def test_sparse_spatial_weights_restate_the_dense_reference_semantics():
+    """tangram/spatial_weights.py:5-30 on CSR: row-L1-normalised distances on the connectivity pattern, +I."""
+    conn, dist = grid_graph(30)
+    ad = tg.MiniAnnData(X=np.ones((30, 2), dtype=np.float32))
+    ad.obsp = {"spatial_connectivities": conn, "spatial_distances": dist}
+    w = sw.spatial_weights(ad, standardized=True, self_inclusion=True).toarray()
+    d = dist.toarray()
+    ref = d / np.abs(d).sum(axis=1, keepdims=True) * (conn.toarray() != 0) + np.eye(30)
+    assert np.allclose(w, ref, atol=1e-6)
+    b = sw.spatial_weights(ad, standardized=False, self_inclusion=False)
+    assert sp.issparse(b) and np.array_equal(b.toarray(), conn.toarray())
+    assert np.allclose(w, spatial_weights_from_graph(conn, dist, True, True).toarray())
+    with pytest.raises(ValueError, match="Missing spatial neighborhood parameters"):
+        sw.spatial_weights(tg.MiniAnnData(X=np.ones((3, 2))), True, True)
+
+
+def _adatas(n=12, v=7, k=5):
+    rng = np.random.default_rng(0)
+    genes = [f"G{i}" for i in range(k)]
+    ad_sc = tg.MiniAnnData(X=rng.random((n, k)).astype(np.float32) + 0.1,
+                           obs=pd.DataFrame({"lab": ["a", "b"] * (n // 2)}, index=[f"c{i}" for i in range(n)]),
+                           var=pd.DataFrame(index=genes))
+    ad_sp = tg.MiniAnnData(X=rng.random((v, k)).astype(np.float32) + 0.1,
+                           obs=pd.DataFrame(index=[f"v{i}" for i in range(v)]), var=pd.DataFrame(index=genes))
+    return ad_sc, ad_sp
+
+
+def test_map_cells_to_space_validation_messages():
+    """mapping_utils.py:206-254: same exceptions and messages, raised before any device work."""
+    ad_sc, ad_sp = _adatas()
+    with pytest.raises(ValueError, match="Missing tangram parameters. Run `pp_adatas\\(\\)`."):
+        tg.map_cells_to_space(ad_sc, ad_sp)
+    tg.pp_adatas(ad_sc, ad_sp)
+    with pytest.raises(ValueError, match="lambda_g1 cannot be 0."):
+        tg.map_cells_to_space(ad_sc, ad_sp, lambda_g1=0)
+    with pytest.raises(ValueError, match="Invalid input for density_prior."):
+        tg.map_cells_to_space(ad_sc, ad_sp, density_prior="bogus")
+    with pytest.raises(ValueError, match="When lambda_d is set, please define the density_prior."):
+        tg.map_cells_to_space(ad_sc, ad_sp, lambda_d=1, density_prior=None)
+    with pytest.raises(ValueError, match='Argument "mode" must be'):
+        tg.map_cells_to_space(ad_sc, ad_sp, mode="nope")
+    with pytest.raises(ValueError, match="A cluster_label must be specified if mode is 'clusters'."):
+        tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters")
+    with pytest.raises(ValueError, match="target_count, lambda_f_reg and lambda_count must be specified"):
+        tg.map_cells_to_space(ad_sc, ad_sp, mode="constrained")
+    with pytest.raises(ValueError, match="Given training genes list should be subset of two AnnDatas."):
+        tg.map_cells_to_space(ad_sc, ad_sp, cv_train_genes=["zzz"])
+    with pytest.raises(NotImplementedError):
+        tg.map_cells_to_space(ad_sc, ad_sp, lambda_moran=1.0)
+    with pytest.raises(NotImplementedError):
+        tg.map_cells_to_space(ad_sc, ad_sp, mode="constrained", target_count=3)
+
+
+def test_all_zero_gene_is_rejected():
+    ad_sc, ad_sp = _adatas()
+    tg.pp_adatas(ad_sc, ad_sp)
+    ad_sp.X[:, 1] = 0.0
+    with pytest.raises(ValueError, match="Genes with all zero values detected"):
+        tg.map_cells_to_space(ad_sc, ad_sp)
+
+
+def test_one_hot_encoding_order_of_first_appearance():
+    """tangram/utils.py:105-123."""
+    df = tg.one_hot_encoding(pd.Series(["b", "a", "b", "c"]))
+    assert list(df.columns) == ["b", "a", "c"]
+    assert df.values.tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1]]
+
+
+def test_mapper_refuses_unsupported_terms_and_cpu():
+    S = np.ones((4, 3), dtype=np.float32)
+    G = np.ones((5, 3), dtype=np.float32)
+    with pytest.raises(NotImplementedError):
+        tg.Mapper(S, G, lambda_geary=1.0)
+    with pytest.raises(NotImplementedError):
+        tg.Mapper(S, G, adata_map=object())
+    with pytest.raises(ValueError, match="B200 GPUs only"):
+        tg.Mapper(S, G, device="cpu")

@@ -21,8 +21,10 @@ eng.run(5)
 lib.tgb200_debug_epi_timing(out, 0)
 v = list(out); n = v[4]
 print("warp-tiles", n)
-names = ["wait_cp_async", "tmem_ld+compute", "writeback", "prefetch_issue", "n", "wait_tfull"]
+names = ["wait_stage_mbar", "tmem_ld+compute", "fence+pair_barrier", "leader_issue(lane1 view)", "n", "wait_tfull"]
 tot = sum(v[i] for i in (0, 1, 2, 3, 5))
 for i in (5, 0, 1, 2, 3):
     print(f"{names[i]:18s} {v[i] / n:10.0f} cycles per warp-tile  {100 * v[i] / tot:5.1f}%")
 print("total per warp-tile", tot / n)
+
+print("leader issue+wait_read per warp-tile", v[6] / max(v[7], 1))
