@@ -34,6 +34,8 @@ WORKLOADS = {
 C5_LAMBDAS = dict(lambda_neighborhood_g1=0.96, lambda_ct_islands=0.17, lambda_getis_ord=0.71,
                   lambda_r=2.95e-9, lambda_l2=1e-18)
 L2_BYTES = 126e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+TRAFFIC = {("c3", "bf16", "gemm_bwd_adam"): None}
 
 
 def peaks():
@@ -279,13 +281,19 @@ def main():
         top = max(avg, key=avg.get)
         Nl = r1 - r0
         sS = 2.0 if a.precision == "bf16" else 4.0
-        # algorithmic work of each contraction kernel: flops, HBM bytes
+        # algorithmic work of each kernel: flops, HBM bytes per launch
+        pb = 2.0 if a.precision == "bf16" else 4.0          # bytes per element of the stored P
         work = {
-            "gemm_fwd": (2.0 * Nl * V * K, (2.0 if a.precision == "bf16" else 4.0) * Nl * V + sS * Nl * K + 4.0 * V * K),
-            "gemm_rowdot": (2.0 * Nl * V * K, (2.0 if a.precision == "bf16" else 4.0) * Nl * V + 4.0 * Nl * K),
+            "gemm_fwd": (2.0 * Nl * V * K, pb * Nl * V + sS * Nl * K + 4.0 * V * K),
+            "gemm_rowdot": (2.0 * Nl * V * K, pb * Nl * V + sS * Nl * K + sS * V * K),
             "gemm_bwd_adam": (2.0 * Nl * V * K, 24.0 * Nl * V + sS * Nl * K + sS * V * K),
-            "softmax_rows": (0.0, (4.0 + (2.0 if a.precision == "bf16" else 4.0)) * Nl * V),
+            "softmax_rows": (0.0, (4.0 + pb) * Nl * V),
+            "loss_reduce": (0.0, 4.0 * V * K * (1 + 1)),
+            "scale_rows": (0.0, 6.0 * Nl * K),
         }
+        known = {k: v for k, v in avg.items() if any(w in k for w in work)}
+        if known:
+            top = max(known, key=known.get)
         key = next((k for k in work if k in top), None)
         if key:
             fl, by = work[key]
@@ -299,8 +307,17 @@ def main():
             else:
                 roof = {"bound": "hbm", "achieved": by / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
             roof["frac"] = roof["achieved"] / roof["peak"]
-            roof.update({"kernel": top, "kernel_ms": avg[top], "share_of_step": avg[top] / step_ms, "traffic": None,
+            roof.update({"kernel": top, "kernel_ms": avg[top], "share_of_step": avg[top] / step_ms, "traffic": TRAFFIC.get((a.workload, a.precision, key)),
                          "peak_source": pk["src"], "per_kernel_ms": avg})
+            # the other contraction kernels against the tensor roofline (explains the step)
+            others = {}
+            for kname, ms in avg.items():
+                kk = next((k for k in ("gemm_fwd", "gemm_rowdot", "gemm_bwd_adam") if k in kname), None)
+                if kk and a.precision == "bf16":
+                    others[kname] = {"tflops": work[kk][0] / (ms / 1e3) / 1e12,
+                                     "frac_of_sustained_bf16_peak": work[kk][0] / (ms / 1e3) / 1e12 / pk["tf_sust"],
+                                     "hbm_GBs": work[kk][1] / (ms / 1e3) / 1e9}
+            roof["contractions"] = others
         hb, fl_it = eng.algorithmic_cost()
         roof_step = max(hb / (pk["hbm"] * 1e9), fl_it / ((pk["tf_sust"] if a.precision == "bf16" else 74.0) * 1e12))
         if roof is not None:
