@@ -151,7 +151,6 @@ struct Csr {
   const float* vals;
 };
 
-constexpr int kLossRows = 64;   // voxel rows per CTA in the reduction kernels
 constexpr int kLossCols = 128;  // gene columns per CTA (= threads)
 
 struct LossParams {
@@ -187,23 +186,37 @@ struct LossParams {
 
 // Y = sum over split partials; per-gene <Y,G>, |Y|^2, colsum(Y) for this row chunk;
 // per-voxel <Y,G>, |Y|^2 for this column chunk (only when lambda_g2 != 0).
+// rows_per_block (<= kLossRowsMax) is chosen on the host so that small problems still fill the GPU
+// and large ones (V = 50k) keep the partial arrays small.
+constexpr int kLossRowsMax = 128;
 __global__ void __launch_bounds__(kLossCols)
-k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_stats) {
-  __shared__ float shr[4][kLossRows][2];
+k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_stats, int rows_per_block) {
+  __shared__ float shr[4][kLossRowsMax][2];
   const int k = blockIdx.x * kLossCols + threadIdx.x;
-  const int j0 = blockIdx.y * kLossRows;
+  const int j0 = blockIdx.y * rows_per_block;
   const size_t plane = (size_t)p.V * p.Ke;
   const bool in = k < p.Ke, gene = k < p.K;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool writeY = nsplit > 1 || part != p.Y;
   float dot = 0.f, ny2 = 0.f, ys = 0.f;
-  for (int r = 0; r < kLossRows; ++r) {
+  const int nrows = min(rows_per_block, p.V - j0);
+  for (int r = 0; r < nrows; ++r) {
     const int j = j0 + r;
-    if (j >= p.V) break;   // uniform across the CTA
     float y = 0.f, g = 0.f;
     if (in) {
       const size_t o = (size_t)j * p.Ke + k;
-      for (int z = 0; z < nsplit; ++z) y += part[z * plane + o];
-      if (nsplit > 1 || part != p.Y) p.Y[o] = y;
+      if (nsplit == 1) {
+        y = part[o];
+      } else {
+        int z = 0;
+        for (; z + 4 <= nsplit; z += 4) {          // independent loads in flight
+          const float a0 = part[(size_t)z * plane + o], a1 = part[(size_t)(z + 1) * plane + o];
+          const float a2 = part[(size_t)(z + 2) * plane + o], a3 = part[(size_t)(z + 3) * plane + o];
+          y += (a0 + a1) + (a2 + a3);
+        }
+        for (; z < nsplit; ++z) y += part[(size_t)z * plane + o];
+      }
+      if (writeY) p.Y[o] = y;
       if (gene) { g = p.G[o]; dot += y * g; ny2 += y * y; ys += y; }
     }
     if (row_stats) {
@@ -218,8 +231,7 @@ k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_
   }
   if (row_stats) {
     __syncthreads();
-    const int r = threadIdx.x;
-    if (r < kLossRows && j0 + r < p.V) {
+    for (int r = threadIdx.x; r < nrows; r += kLossCols) {
       float a = shr[0][r][0] + shr[1][r][0] + shr[2][r][0] + shr[3][r][0];
       float b = shr[0][r][1] + shr[1][r][1] + shr[2][r][1] + shr[3][r][1];
       float* rp = p.rowpart + ((size_t)blockIdx.x * p.V + (j0 + r)) * 2;
@@ -228,16 +240,31 @@ k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_
   }
 }
 
+// out[c][k] = sum over row chunks of part[chunk][c][k]   (thread per gene, coalesced, deterministic order)
+__global__ void k_col_finalize(const float* __restrict__ part, int nchunk, int ncomp, int Ke, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (k >= Ke) return;
+  float s0 = 0.f, s1 = 0.f;
+  int q = 0;
+  for (; q + 2 <= nchunk; q += 2) {
+    s0 += part[((size_t)q * ncomp + c) * Ke + k];
+    s1 += part[((size_t)(q + 1) * ncomp + c) * Ke + k];
+  }
+  if (q < nchunk) s0 += part[((size_t)q * ncomp + c) * Ke + k];
+  out[(size_t)c * Ke + k] = s0 + s1;
+}
+
 // Zout = Op @ Y (CSR, ~7 nnz/row) fused with the per-gene <Zout,REF>, |Zout|^2 partials.
 // Replaces the dense (V x V) @ (V x K) SGEMMs at :235 and :171.
 __global__ void __launch_bounds__(kLossCols)
 k_spatial_colstats(int V, int K, int Ke, Csr op, const float* __restrict__ Y, const float* __restrict__ REF,
-                   float* __restrict__ Zout, float* __restrict__ colpart2) {
+                   float* __restrict__ Zout, float* __restrict__ colpart2, int rows_per_block) {
   const int k = blockIdx.x * kLossCols + threadIdx.x;
-  const int j0 = blockIdx.y * kLossRows;
+  const int j0 = blockIdx.y * rows_per_block;
   const bool gene = k < K;
   float dot = 0.f, nz2 = 0.f;
-  for (int r = 0; r < kLossRows; ++r) {
+  for (int r = 0; r < rows_per_block; ++r) {
     const int j = j0 + r;
     if (j >= V) break;
     if (gene) {
@@ -431,7 +458,7 @@ k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ 
       acc -= p.FT.vals[e] * p.H[(size_t)p.FT.indices[e] * p.T + t];
     dy = p.lam_ct * acc / ((float)p.V * (float)p.T);
   }
-  dY[o] = dy;
+  if (dY != nullptr) dY[o] = dy;
   if (dYb != nullptr) dYb[o] = __float2bfloat16_rn(dy);
 }
 

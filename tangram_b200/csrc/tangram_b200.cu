@@ -103,7 +103,8 @@ struct tgb200_mapper {
   DevBuf<float> colpart, colpart_nb, colpart_go, rowpart, ctpart;
   DevBuf<float> coefA, coefB, coefAn, coefBn, coefAg, coefBg, coefAr, coefBr, densg;
   CsrDev W, WT, F, FT, A, AT;
-  int nchunk = 0, ncolchunk = 0, n_ct_blocks = 0;
+  int nchunk = 0, ncolchunk = 0, n_ct_blocks = 0, loss_rows = 16;
+  DevBuf<float> colfin;         // finalised per-gene sums: [3 | 2 | 2][Ke]
   // history
   DevBuf<float> hist;
   int64_t hist_len = 0, hist_cap = 0;
@@ -214,7 +215,11 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   h->r_parts = (int)ceil_div(h->Ke, h->bf16 ? TC_RDOT_BN : SG_BN) * h->rd_splits;
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
-  h->nchunk = (int)ceil_div(h->V, kLossRows);
+  // voxel rows per CTA of the loss reductions: enough CTAs for small V, bounded partial arrays for large V
+  h->loss_rows = 16;
+  while (ceil_div(h->V, h->loss_rows) > 512 && h->loss_rows < kLossRowsMax) h->loss_rows += 16;
+  h->nchunk = (int)ceil_div(h->V, h->loss_rows);
+  A(h->colfin.alloc((size_t)7 * h->Ke));
   h->ncolchunk = (int)ceil_div(h->Ke, kLossCols);
   A(h->colpart.alloc((size_t)h->nchunk * 3 * h->Ke));
   A(h->coefA.alloc(h->Ke)); A(h->coefB.alloc(h->Ke));
@@ -560,24 +565,35 @@ static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool re
   dim3 rgrid(h->ncolchunk, h->nchunk);
   const float* part = (h->fwd_splits > 1 && reduce_partials_first) ? h->Ypart.p : h->Y.p;
   const int nsplit = (h->fwd_splits > 1 && reduce_partials_first) ? h->fwd_splits : 1;
-  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, nsplit, c.lambda_g2 != 0.f ? 1 : 0);
+  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, nsplit, c.lambda_g2 != 0.f ? 1 : 0, h->loss_rows);
   LAUNCH_CHECK("loss_reduce");
+  const dim3 fgrid3((unsigned)ceil_div(h->Ke, 128), 3), fgrid2((unsigned)ceil_div(h->Ke, 128), 2);
+  k_col_finalize<<<fgrid3, 128, 0, s>>>(h->colpart.p, h->nchunk, 3, h->Ke, h->colfin.p);
+  LAUNCH_CHECK("col_finalize");
+  p.colpart = h->colfin.p;
   if (c.lambda_neighborhood_g1 > 0.f) {
-    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->W.view(), h->Y.p, h->WG.p, h->Z.p, h->colpart_nb.p);
+    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->W.view(), h->Y.p, h->WG.p, h->Z.p, h->colpart_nb.p, h->loss_rows);
     LAUNCH_CHECK("spatial_colstats");
+    k_col_finalize<<<fgrid2, 128, 0, s>>>(h->colpart_nb.p, h->nchunk, 2, h->Ke, h->colfin.p + (size_t)3 * h->Ke);
+    LAUNCH_CHECK("col_finalize");
+    p.colpart_nb = h->colfin.p + (size_t)3 * h->Ke;
   }
   if (c.lambda_getis_ord > 0.f) {
-    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->A.view(), h->Y.p, h->AG.p, h->Zg.p, h->colpart_go.p);
+    k_spatial_colstats<<<rgrid, kLossCols, 0, s>>>(h->V, h->K, h->Ke, h->A.view(), h->Y.p, h->AG.p, h->Zg.p, h->colpart_go.p, h->loss_rows);
     LAUNCH_CHECK("spatial_colstats");
+    k_col_finalize<<<fgrid2, 128, 0, s>>>(h->colpart_go.p, h->nchunk, 2, h->Ke, h->colfin.p + (size_t)5 * h->Ke);
+    LAUNCH_CHECK("col_finalize");
+    p.colpart_go = h->colfin.p + (size_t)5 * h->Ke;
   }
   if (c.lambda_ct_islands > 0.f) {
     k_ct_islands<<<h->n_ct_blocks, 256, 0, s>>>(p);
     LAUNCH_CHECK("ct_islands");
   }
-  k_loss_scalars<<<1, 1024, 0, s>>>(p, h->nchunk, h->ncolchunk, hist_row);
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->ncolchunk, hist_row);
   LAUNCH_CHECK("loss_scalars");
   dim3 dgrid(h->ncolchunk, h->V);
-  k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->dY.p, h->bf16 ? h->dYb.p : nullptr);
+  // the tensor-core path consumes only the bf16 copy of dY_ext
+  k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->bf16 ? nullptr : h->dY.p, h->bf16 ? h->dYb.p : nullptr);
   LAUNCH_CHECK("dy_assemble");
   return TGB200_OK;
 }
@@ -772,11 +788,14 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   p.lam_g2 = 1.f; p.lam_g1 = 1.f; p.lam_nb = 0.f; p.lam_go = 0.f; p.lam_ct = 0.f; p.density_mode = 0;
   dim3 rgrid(h->ncolchunk, h->nchunk);
   const float* part = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
-  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, h->fwd_splits, 1);
+  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, h->fwd_splits, 1, h->loss_rows);
   LAUNCH_CHECK("loss_reduce");
+  k_col_finalize<<<dim3((unsigned)ceil_div(h->Ke, 128), 3), 128, 0, s>>>(h->colpart.p, h->nchunk, 3, h->Ke, h->colfin.p);
+  LAUNCH_CHECK("col_finalize");
+  p.colpart = h->colfin.p;
   k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, nullptr, h->N, h->Y.p + (size_t)h->V * h->Ke);
   LAUNCH_CHECK("row_scalar_reduce");
-  k_loss_scalars<<<1, 1024, 0, s>>>(p, h->nchunk, h->ncolchunk, hist.p);
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->ncolchunk, hist.p);
   LAUNCH_CHECK("loss_scalars");
   // sparsity-weighted gene score needs per-gene cosines: recover them from coefA/coefB on the host
   std::vector<float> hrow(TGB200_HIST_COLS), cA(h->K), cB(h->K), Gh((size_t)h->V * h->Ke), tail(4);
@@ -851,7 +870,17 @@ extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* ou
   int64_t cnt = 0;
   const int64_t vk = (int64_t)h->V * h->Ke;
   if (nm == "Y") { src = h->Y.p; cnt = vk; }
-  else if (nm == "dY") { src = h->dY.p; cnt = vk; }
+  else if (nm == "dY") {
+    src = h->dY.p; cnt = vk;
+    if (h->bf16 && out_host) {     // only the bf16 copy exists on the tensor-core path
+      std::vector<__nv_bfloat16> tmp((size_t)vk);
+      if (cap < cnt) return fail(TGB200_ERR_INVALID, "buffer 'dY' needs %lld floats", (long long)cnt);
+      CK(cudaMemcpy(tmp.data(), h->dYb.p, (size_t)vk * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < vk; ++i) out_host[i] = __bfloat162float(tmp[(size_t)i]);
+      *n = cnt;
+      return TGB200_OK;
+    }
+  }
   else if (nm == "rdot") { src = h->rdot.p; cnt = h->N; }
   else if (nm == "Sx") { src = h->Sx.p; cnt = (int64_t)h->N * h->Ke; }
   else if (nm == "shape") {   // Ke, ld, fwd_splits, r_parts
