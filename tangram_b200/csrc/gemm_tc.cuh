@@ -78,6 +78,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -313,13 +316,20 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+#ifndef TGB_EPI_NBUF
+#define TGB_EPI_NBUF 1
+#endif
+#ifndef TGB_EPI_L2_AHEAD
+#define TGB_EPI_L2_AHEAD 1      // sub-tiles prefetched into L2 ahead of the staged ones
+#endif
 struct TcEpiAdam {
   TcAdamArgs p; int M;
   static constexpr int CW = 16;                            // columns per warp per staged sub-tile
   static constexpr int SW = 32;                            // staged sub-tile width (two warps)
   static constexpr int kArrayBytes = 32 * SW * 4;          // 32 rows x 128 B = 4 KB
   static constexpr int kBufBytes = 3 * kArrayBytes;        // M, m, v
-  static constexpr int kGroupBytes = 2 * kBufBytes;        // double buffered: 24 KB per group
+  static constexpr int NBUF = TGB_EPI_NBUF;                // staging depth per lane quarter
+  static constexpr int kGroupBytes = NBUF * kBufBytes;
   static constexpr int kStagingBytes = 4 * kGroupBytes;    // 4 lane quarters
   // TMA SWIZZLE_128B: 16-byte chunk jj of row r lives at chunk position jj ^ (r & 7)
   static __device__ __forceinline__ uint32_t swz(int r, int jj) { return (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4)); }
@@ -345,6 +355,11 @@ struct TcEpiAdam {
     if (p.l1part) { l1s += fabsf(xn); l2s = fmaf(xn, xn, l2s); }
     return pt;
   }
+  // Configuration measured on B200 at 100k x 10k x 2k (tools/mainloop_only.py, ms per backward launch):
+//   BN=128 ring 4x32KB staging 2-deep: 7.02   BN=128 5x32KB 1-deep: 6.79   BN=256 3x48KB 1-deep: 6.62
+//   BN=256 3x48KB 1-deep + L2 prefetch 1 ahead: 6.36 (chosen)   2 ahead: 6.87   BN=256 2x48KB 2-deep: 7.58
+// The L2->SM operand stream (A is re-read per column tile) competes with 26 B/element of state traffic,
+// so the wider tile (25% fewer operand bytes) and a deeper ring beat a deeper staging pipeline.
   // leader lane of a group: three bulk tensor loads of sub-tile `c` into staging buffer `b`
   __device__ __forceinline__ void issue_loads(const EpiCtx& cx, int g, int b, int row0, int col) const {
     const uint32_t bar = cx.bars + (uint32_t)(g * 2 + b) * 8u;
@@ -353,6 +368,15 @@ struct TcEpiAdam {
     tma_load_2d_u32(cx.map[0], bar, dst, col, row0, kPolicyEvictFirst);
     tma_load_2d_u32(cx.map[1], bar, dst + kArrayBytes, col, row0, kPolicyEvictFirst);
     tma_load_2d_u32(cx.map[2], bar, dst + 2 * kArrayBytes, col, row0, kPolicyEvictFirst);
+  }
+  // DRAM -> L2 prefetch of a sub-tile a short, fixed distance ahead of its bulk load (a few microseconds:
+  // long enough to hide DRAM latency, short enough that the lines are still in L2 when the load arrives)
+  __device__ __forceinline__ void prefetch_l2(const EpiCtx& cx, int row0, int col) const {
+    if (col < p.V) {
+      tma_prefetch_l2_2d(cx.map[0], col, row0);
+      tma_prefetch_l2_2d(cx.map[1], col, row0);
+      tma_prefetch_l2_2d(cx.map[2], col, row0);
+    }
   }
   __device__ __forceinline__ void issue_stores(const EpiCtx& cx, int g, int b, int row0, int col) const {
     const uint32_t src = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
@@ -368,7 +392,8 @@ struct TcEpiAdam {
     static_assert(NW == 8, "two warps per TMEM lane quarter");
     if (ew < 4 && lane == 0) {
       issue_loads(cx, q, 0, t.m0 + q * 32, t.n0);
-      issue_loads(cx, q, 1, t.m0 + q * 32, t.n0 + SW);
+      if (NBUF > 1) issue_loads(cx, q, 1, t.m0 + q * 32, t.n0 + SW);
+      for (int k = 0; k < TGB_EPI_L2_AHEAD; ++k) prefetch_l2(cx, t.m0 + q * 32, t.n0 + (NBUF + k) * SW);
     }
   }
   __device__ __forceinline__ void finish(int ew, int lane, int) const {
@@ -474,7 +499,7 @@ struct TcEpiAdam {
     TGB_T0();
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c) {
-      const int b = c & 1;
+      const int b = (NBUF > 1) ? (c & 1) : 0;
       const uint32_t buf = cx.staging + (uint32_t)(q * kGroupBytes + b * kBufBytes);
       const int colg = t.n0 + c * SW;             // first column of the staged sub-tile
       const int col0 = colg + part * CW;          // first column this warp updates
@@ -497,10 +522,12 @@ struct TcEpiAdam {
       TGB_TICK(tb);
       if (leader) {
         issue_stores(cx, q, b, row0, colg);
-        if (c + 2 < NCHUNK) {
+        if (c + NBUF < NCHUNK) {
           bulk_wait_read0();                      // the store has read the buffer: refill it
-          issue_loads(cx, q, b, row0, colg + 2 * SW);
+          issue_loads(cx, q, b, row0, colg + NBUF * SW);
         }
+        if (TGB_EPI_L2_AHEAD > 0 && c + NBUF + TGB_EPI_L2_AHEAD < NCHUNK)
+          prefetch_l2(cx, row0, colg + (NBUF + TGB_EPI_L2_AHEAD) * SW);
       }
       TGB_TICK(tp);
     }
@@ -738,7 +765,13 @@ static inline int tc_check_launch(const char* name, char* err, size_t n) {
 }
 
 constexpr int TC_FWD_BN = 256, TC_FWD_STAGES = 4;
-constexpr int TC_BWD_BN = 128, TC_BWD_STAGES = 4, TC_BWD_EPI_WARPS = 8;
+#ifndef TGB_BWD_STAGES
+#define TGB_BWD_STAGES 3
+#endif
+#ifndef TGB_BWD_BN
+#define TGB_BWD_BN 256
+#endif
+constexpr int TC_BWD_BN = TGB_BWD_BN, TC_BWD_STAGES = TGB_BWD_STAGES, TC_BWD_EPI_WARPS = 8;
 constexpr int TC_RD_STAGES = 4;
 
 static inline int tc_splits(long long tiles, long long k_total, int min_k) {

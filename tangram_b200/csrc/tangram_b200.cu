@@ -900,6 +900,39 @@ extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* ou
 }
 
 #ifdef TGB_EPI_TIMING
+// Dev microbenchmark: the state traffic of the backward epilogue as a pure streaming kernel
+// (read M, m, v; write M, m, v and bf16 P) -- the practical HBM ceiling for that access mix.
+__global__ void __launch_bounds__(256) k_stream_adam(float4* __restrict__ M, float4* __restrict__ m, float4* __restrict__ v,
+                                                      uint2* __restrict__ P, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 x = ld_stream(M + i), a = ld_stream(m + i), b = ld_stream(v + i);
+    float* xs = reinterpret_cast<float*>(&x); float* as = reinterpret_cast<float*>(&a); float* bs = reinterpret_cast<float*>(&b);
+    float pr[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float g = xs[e] * 1e-3f;
+      as[e] = fmaf(g - as[e], 0.1f, as[e]);
+      bs[e] = fmaf(0.001f * g, g, bs[e] * 0.999f);
+      xs[e] = fmaf(-0.1f * as[e], fast_rcp(fmaf(fast_sqrt(bs[e]), 1.f, 1e-8f)), xs[e]);
+      pr[e] = fast_ex2(xs[e] - 20.f);
+    }
+    st_stream(M + i, x); st_stream(m + i, a); st_stream(v + i, b);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(pr[0], pr[1]), hi = __floats2bfloat162_rn(pr[2], pr[3]);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+    P[i] = u;
+  }
+}
+extern "C" __attribute__((visibility("default"))) int tgb200_debug_stream_bench(tgb200_mapper* h, int blocks_per_sm, float* ms_out) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const size_t n4 = (size_t)h->N * h->ld / 4;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_stream_adam<<<148 * blocks_per_sm, 256>>>((float4*)h->M.p, (float4*)h->m.p, (float4*)h->v.p, (uint2*)h->Pb.p, n4);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(ms_out, e0, e1);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
 extern "C" __attribute__((visibility("default"))) int tgb200_debug_epi_timing(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(unsigned long long) * 8);

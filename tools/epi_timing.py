@@ -5,7 +5,7 @@ import ctypes, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tangram_b200 import _build, _lib
-_build.LIB = os.path.join(ROOT, "tools", "libtiming.so")
+_build.LIB = os.path.join(ROOT, "tools", os.environ.get("TGB_DBG_LIB", "libtiming.so"))
 _build.is_current = lambda: True
 from tangram_b200.engine import Engine
 import bench
