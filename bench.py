@@ -35,7 +35,8 @@ C5_LAMBDAS = dict(lambda_neighborhood_g1=0.96, lambda_ct_islands=0.17, lambda_ge
                   lambda_r=2.95e-9, lambda_l2=1e-18)
 L2_BYTES = 126e6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-TRAFFIC = {("c3", "bf16", "gemm_bwd_adam"): None}
+TRAFFIC = {("c3", "bf16", "gemm_bwd_adam"): 31.81e9,      # profiles/r01_final_c3_gemm_kernels_raw.csv
+           ("c3", "bf16", "gemm_fwd"): 4.22e9, ("c3", "bf16", "gemm_rowdot"): 4.09e9}
 
 
 def peaks():
