@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (cells, voxels, genes, types, clusters-mode, description)
+    "c1": (26_431, 9_852, 249, 0, False,
+           "reference fixtures data/test_ad_sc.h5ad x data/test_ad_sp.h5ad (tests/golden/c1_reference.npz), mode=cells"),
     "c2": (10_000, 1_000, 1_000, 0, False, "synthetic 10k cells x 1k voxels x 1k genes, mode=cells"),
     "c3": (100_000, 10_000, 2_000, 0, False, "synthetic 100k cells x 10k voxels x 2k genes, mode=cells"),
     "c4": (256, 50_000, 5_000, 0, True, "synthetic 256 clusters x 50k voxels x 5k genes, mode=clusters"),
@@ -51,6 +53,11 @@ def peaks():
 def gen_inputs(name, r0, r1, seed=0):
     """Rows [r0, r1) of the synthetic workload (S rows are generated per block so that ranks agree)."""
     N, V, K, T, clusters, _ = WORKLOADS[name]
+    if name == "c1":      # real data: the reference's own test fixtures, exported by tests/golden/make_c1_golden.py
+        import scipy.sparse as sp
+        z = np.load(os.path.join(ROOT, "tests", "golden", "c1_reference.npz"))
+        S = sp.csr_matrix((z["S_data"], z["S_indices"], z["S_indptr"]), shape=tuple(z["S_shape"]))[r0:r1].toarray()
+        return dict(S=np.ascontiguousarray(S, dtype=np.float32), G=z["G"], d=z["d"])
     rng = np.random.default_rng(seed)
     G = np.log1p(rng.poisson(2.0, (V, K))).astype(np.float32)
     G[:, ~G.any(axis=0)] = 1.0

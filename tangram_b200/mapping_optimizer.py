@@ -55,6 +55,26 @@ def _to_csr(mat, n):
             np.ascontiguousarray(csr.data, dtype=np.float32))
 
 
+def _pinned_empty(shape):
+    """float32 ndarray backed by page-locked host memory when torch can provide it (the N x V result is
+    the largest device->host copy of the whole call; pageable memory halves its bandwidth)."""
+    try:
+        import torch
+        if int(np.prod(shape)) * 4 >= (64 << 20):
+            t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            a = t.numpy()
+            _PINNED_KEEPALIVE[id(a)] = t     # the tensor owns the allocation
+            import weakref
+            weakref.finalize(a, _PINNED_KEEPALIVE.pop, id(a), None)
+            return a
+    except Exception:  # noqa: BLE001
+        pass
+    return np.empty(shape, dtype=np.float32)
+
+
+_PINNED_KEEPALIVE = {}
+
+
 def format_terms(row):
     """The reference's print line (mapping_optimizer.py:300-307) from one history row."""
     msg = ["{}: {:.3f}".format(name, row[c]) for c, name in _PRINT_TERMS if not np.isnan(row[c])]
@@ -285,7 +305,7 @@ class Mapper:
         for c, key in enumerate(_HIST_KEYS[1:], start=1):
             training_history[key] = [float(x) for x in rows[:, c]]
         self.history_matrix = rows
-        output = np.empty((self.n_cells, self.n_voxels), dtype=np.float32)
+        output = _pinned_empty((self.n_cells, self.n_voxels))
         _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(output), None))
         return output, training_history
 

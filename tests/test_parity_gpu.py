@@ -197,3 +197,38 @@ def test_map_cells_to_space_api_end_to_end():
     ad_map_c = tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters", cluster_label="lab", device="cuda:0",
                                      num_epochs=10, random_state=3, verbose=False)
     assert ad_map_c.X.shape == (3, V)
+
+
+def _load_c1():
+    import os
+    import scipy.sparse as sp
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_reference.npz"))
+    S = sp.csr_matrix((z["S_data"], z["S_indices"], z["S_indptr"]), shape=tuple(z["S_shape"])).toarray().astype(np.float32)
+    return z, S
+
+
+def test_baseline_config1_real_data_against_reference_run():
+    """BASELINE config 1: the reference's own fixtures (26431 cells x 9852 voxels x 249 genes, mode='cells',
+    100 epochs, random_state=42).  Golden = the REAL reference Mapper run on the CPU (tests/golden/make_c1_golden.py,
+    535 s on 8 cores); the CUDA fp32 path must match its loss trajectory and mapping rows within 1e-4."""
+    z, S = _load_c1()
+    m = _mapper(S=S, G=z["G"], d=z["d"], lambda_g1=1, lambda_d=1, random_state=int(z["seed"]))
+    out, hist = m.train(int(z["epochs"]), print_each=None)
+    tl = np.array([float(x) for x in hist["total_loss"]])
+    assert max_rel(tl, z["total_loss"]) < 1e-4
+    assert max_rel(hist["main_loss"], z["main_loss"]) < 1e-4
+    assert max_rel(hist["kl_reg"], z["kl_reg"]) < 2e-3
+    assert rel_fro(out[z["rows"]], z["out_rows"]) < 1e-4
+    assert rel_fro(out.sum(axis=0), z["out_colsum"]) < 1e-5
+    assert np.mean(out.argmax(axis=1) == z["out_rowmax_idx"]) > 0.999
+
+
+def test_baseline_config1_real_data_bf16_tracks_reference():
+    z, S = _load_c1()
+    from tangram_b200 import Mapper
+    m = Mapper(device="cuda:0", S=S, G=z["G"], d=z["d"], lambda_g1=1, lambda_d=1, random_state=int(z["seed"]), precision="bf16")
+    out, hist = m.train(int(z["epochs"]), print_each=None)
+    tl = np.array([float(x) for x in hist["total_loss"]])
+    assert max_rel(tl, z["total_loss"]) < 1e-3
+    assert rel_fro(out.sum(axis=0), z["out_colsum"]) < 5e-3
+    assert np.mean(out.argmax(axis=1) == z["out_rowmax_idx"]) > 0.9
