@@ -44,7 +44,8 @@ typedef enum tgb200_status {
 /* Arithmetic of the two contractions (softmax(M)^T S and S dY^T). */
 typedef enum tgb200_precision {
   TGB200_PREC_FP32 = 0,  /* fp32 FFMA contraction: parity mode (reference is fp32, TF32 off) */
-  TGB200_PREC_BF16 = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
+  TGB200_PREC_BF16 = 1,  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
+  TGB200_PREC_BF16X3 = 2 /* parity mode on tensor cores: each fp32 operand = 3 bf16 planes, 6 partial products */
 } tgb200_precision;
 
 /* mapping_optimizer.py:212-221: which density term is active. */

@@ -8,7 +8,7 @@ import numpy as np
 from . import _build
 
 HIST_COLS = 16
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 DENSITY_NONE, DENSITY_CELLS, DENSITY_SOURCE = 0, 1, 2
 GRAPH_VOXEL_WEIGHTS, GRAPH_NEIGHBORHOOD_FILTER, GRAPH_SPATIAL_WEIGHTS = 0, 1, 2
 

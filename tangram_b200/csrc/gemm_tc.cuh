@@ -247,6 +247,7 @@ struct TcEpiStore {
 
 struct TcEpiRowDot {
   const __nv_bfloat16* S; int lds; float* rpart; int M;
+  const float* Sf;       // parity mode: dot against the fp32 S_ext instead of its bf16 copy
   static constexpr int kStagingBytes = 0;
   template <int BN, int NW>
   __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, EpiCtx&) const {}
@@ -261,7 +262,15 @@ struct TcEpiRowDot {
       float v[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       const int col = t.n0 + c;
-      if (row < M && col < lds) {
+      if (row < M && col < lds && Sf != nullptr) {
+        const float4* src = reinterpret_cast<const float4*>(Sf + (size_t)row * lds + col);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 u = src[h];
+          acc = fmaf(v[4 * h + 0], u.x, acc); acc = fmaf(v[4 * h + 1], u.y, acc);
+          acc = fmaf(v[4 * h + 2], u.z, acc); acc = fmaf(v[4 * h + 3], u.w, acc);
+        }
+      } else if (row < M && col < lds) {
         const uint4* src = reinterpret_cast<const uint4*>(S + (size_t)row * lds + col);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -289,6 +298,9 @@ struct TcAdamArgs {
   const RowConst* rowc;
   float lam_r, lam_l1, lam_l2;
   AdamScalars a;
+  // parity mode (bf16x3): IEEE math in the reference's op order, P from the row-pass statistics
+  const RowStat* stats;   // non-null selects the exact epilogue
+  const float* rdot;
   // next iteration's forward operand and its per-row partial sums (see k_row_norm)
   __nv_bfloat16* Pt;      // N x ld, Pt_ij = exp(Mnew_ij - lse_i)
   float* zpart;           // [n_col_parts][N]
@@ -449,6 +461,32 @@ struct TcEpiAdam {
     dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
     dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
   }
+  // parity-mode update of one 16-column sub-tile: same arithmetic as the FFMA path's EpiAdam (gemm_simt.cuh)
+  __device__ __forceinline__ float one_exact(float x, float dp, float& m, float& v, const RowStat& st, float r) const {
+    const float pr = softmax_prob(x, st);
+    float g = dp - r;
+    if (p.lam_r != 0.f) g -= p.lam_r * (((x - st.mx) - st.log_z) - st.h);
+    g *= pr;
+    if (p.lam_l1 != 0.f) g += p.lam_l1 * (float)((x > 0.f) - (x < 0.f));
+    if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x;
+    return adam_update(x, g, m, v, p.a);
+  }
+  __device__ __forceinline__ void update_chunk_exact(uint32_t buf, int jbase, int lane, int col0, const float (&acc)[16],
+                                                     const RowStat& st, float r) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t sp = buf + swz(lane, jbase + j);
+      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
+      const int col = col0 + 4 * j;
+      if (col + 0 < p.V) x.x = one_exact(x.x, acc[4 * j + 0], m.x, v.x, st, r);
+      if (col + 1 < p.V) x.y = one_exact(x.y, acc[4 * j + 1], m.y, v.y, st, r);
+      if (col + 2 < p.V) x.z = one_exact(x.z, acc[4 * j + 2], m.z, v.z, st, r);
+      if (col + 3 < p.V) x.w = one_exact(x.w, acc[4 * j + 3], m.w, v.w, st, r);
+      sts128(sp, x);
+      sts128(sp + kArrayBytes, m);
+      sts128(sp + 2 * kArrayBytes, v);
+    }
+  }
   // one 16-column sub-tile, thread = row.  GUARD=false: all 16 columns are real voxels.
   template <bool GUARD>
   __device__ __forceinline__ void update_chunk(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[16],
@@ -488,8 +526,14 @@ struct TcEpiAdam {
     const bool leader = (part == 0) && (lane == 0);
     const int row0 = t.m0 + q * 32;
     const int row = row0 + lane;
+    const bool exact = p.stats != nullptr;
     RowConst rc = {0.f, 0.f, 0.f, 0.f};
-    if (row < M) rc = p.rowc[row];
+    RowStat st = {0.f, 1.f, 0.f, 0.f};
+    float rex = 0.f;
+    if (row < M) {
+      if (exact) { st = p.stats[row]; rex = p.rdot[row]; }
+      else rc = p.rowc[row];
+    }
     const float lse_l2e = rc.lse * 1.4426950408889634f;
     float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
     const bool plain = p.lam_r == 0.f && p.lam_l1 == 0.f && p.lam_l2 == 0.f;   // default loss: packed fast path
@@ -508,7 +552,9 @@ struct TcEpiAdam {
       TGB_TICK(tw);
       float acc[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
-      if (row < M && col0 < p.ld) {
+      if (exact) {
+        if (row < M && col0 < p.V) update_chunk_exact(buf, part * 4, lane, col0, acc, st, rex);
+      } else if (row < M && col0 < p.ld) {
         if (col0 + CW <= p.V) {
           if (plain) update_chunk_fast(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs);
           else update_chunk<false>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
@@ -540,7 +586,7 @@ struct TcEpiAdam {
     }
     if (leader) { atomicAdd(&g_epi_timing[6], (unsigned long long)tp); atomicAdd(&g_epi_timing[7], 1ull); }
 #endif
-    if (row < M) {
+    if (row < M && !exact) {
       const size_t o = ((size_t)t.tile_n * 2 + part) * M + row;
       p.zpart[o] = zs;
       if (p.pxpart) p.pxpart[o] = pxs;
@@ -549,12 +595,22 @@ struct TcEpiAdam {
   }
 };
 
+// ---- split-precision operands -------------------------------------------------------------------
+// Parity mode on tensor cores ("bf16x3"): every fp32 operand value x is stored as three bf16 planes
+// hi + mid + lo (x reconstructed to ~2^-24), and a*b is accumulated in fp32 from the six partial products
+// whose magnitude is >= 2^-24 relative: (l,h) (h,l) (m,m) (m,h) (h,m) (h,h), smallest first.  The kernel
+// simply runs its k-loop once per pair into the same TMEM accumulator; with n_pairs == 1 only (h,h) runs
+// (plain bf16 mode).
+struct TcMaps { CUtensorMap m[3]; };
+__device__ __constant__ int kPairA[6] = {2, 0, 1, 1, 0, 0};
+__device__ __constant__ int kPairB[6] = {0, 2, 1, 0, 1, 0};
+
 // ---- the kernel -------------------------------------------------------------------------------
 // Work item w -> (split z, row tile, column tile), column tile fastest so that CTAs running at the
 // same time share A rows and stream B through L2.
 template <bool A_KMAJOR, bool B_KMAJOR, int BN, int STAGES, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
           const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
           const __grid_constant__ CUtensorMap map_e2,
           int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, uint64_t policy_a, uint64_t policy_b,
@@ -579,8 +635,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int total = tiles_m * tiles_n * splits;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&maps_a.m[0]);
+    tma_prefetch_desc(&maps_b.m[0]);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
@@ -607,16 +663,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int k_begin = z * k_per_split;
         const int k_end = min(k_total, k_begin + k_per_split);
         const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
-          const int s = kbg % STAGES;
-          const uint32_t ph = (kbg / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * kStageBytes;
-          uint8_t* sb = sa + TileA::kBytes;
-          mbar_expect_tx(&full_bar[s], kStageBytes);
-          const int k0 = k_begin + kb * TC_BK;
-          TileA::load(&map_a, &full_bar[s], sa, m0, k0, policy_a);
-          TileB::load(&map_b, &full_bar[s], sb, n0, k0, policy_b);
+        for (int pr = 6 - n_pairs; pr < 6; ++pr) {
+          const CUtensorMap* ma = &maps_a.m[kPairA[pr]];
+          const CUtensorMap* mb = &maps_b.m[kPairB[pr]];
+          for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+            const int s = kbg % STAGES;
+            const uint32_t ph = (kbg / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * kStageBytes;
+            uint8_t* sb = sa + TileA::kBytes;
+            mbar_expect_tx(&full_bar[s], kStageBytes);
+            const int k0 = k_begin + kb * TC_BK;
+            TileA::load(ma, &full_bar[s], sa, m0, k0, policy_a);
+            TileB::load(mb, &full_bar[s], sb, n0, k0, policy_b);
+          }
         }
       }
     }
@@ -634,7 +694,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(&tempty_bar[b], (((uint32_t)it >> 1) & 1) ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+        const int total_kb = num_kb * n_pairs;
+        for (int kb = 0; kb < total_kb; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -783,6 +844,16 @@ static inline int tc_splits(long long tiles, long long k_total, int min_k) {
   const long long kps = ((k_total + s - 1) / s + TC_BK - 1) / TC_BK * TC_BK;
   return (int)((k_total + kps - 1) / kps);
 }
+// Parity mode: the tensor core accumulates in fp32 with truncation, a bias that grows with the length of the
+// accumulation chain (measured on real data: -5.6e-6 relative at 6.6k-deep chains, -0.9e-6 at 1.6k).  Chains are
+// therefore cut at `max_chain` contraction elements; the partial results are summed in fp32 (round-to-nearest) by
+// the kernels that consume them.
+static inline int tc_splits_for_chain(long long k_total, int max_chain) {
+  long long s = (k_total + max_chain - 1) / max_chain;
+  if (s < 1) s = 1;
+  const long long kps = ((k_total + s - 1) / s + TC_BK - 1) / TC_BK * TC_BK;
+  return (int)((k_total + kps - 1) / kps);
+}
 static inline int tc_forward_splits(int N, int V, int Ke) {
   return tc_splits((long long)ceil_div(V, TC_BM) * ceil_div(Ke, TC_FWD_BN), N, 512);
 }
@@ -798,42 +869,59 @@ static inline unsigned tc_grid(const TcContext& tc, long long total) {
   return (unsigned)(total < tc.num_sms ? total : tc.num_sms);
 }
 
+// Operand planes: plane p of an operand starts at base + p * plane_elems (bf16).  n_pairs = 1 uses plane 0 only.
+static inline int tc_make_maps(TcContext& tc, TcMaps* maps, const __nv_bfloat16* base, size_t plane_elems, int n_planes,
+                               uint64_t cols, uint64_t rows, uint64_t ld, uint32_t bi, uint32_t bo, char* err, size_t n) {
+  for (int p = 0; p < 3; ++p) {
+    const __nv_bfloat16* ptr = base + (size_t)(p < n_planes ? p : 0) * plane_elems;
+    if (tc_make_map(tc, &maps->m[p], ptr, cols, rows, ld, bi, bo, err, n)) return -2;
+  }
+  return 0;
+}
+
 // Y_ext[z] (V x Ke) = P[cells of split z]^T S_ext[...]
-static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, const __nv_bfloat16* Sx, float* out, int N, int V,
-                             int Ke, int ld, int splits, cudaStream_t s, char* err, size_t n) {
-  CUtensorMap ma, mb;
-  if (tc_make_map(tc, &ma, P, V, N, ld, 64, 64, err, n)) return -2;      // A: MN-major (voxels contiguous), rows = cells
-  if (tc_make_map(tc, &mb, Sx, Ke, N, Ke, 64, 64, err, n)) return -2;    // B: MN-major (genes contiguous), rows = cells
+static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* Sx, size_t s_plane,
+                             int n_pairs, float* out, int N, int V, int Ke, int ld, int splits, cudaStream_t s, char* err,
+                             size_t n) {
+  TcMaps ma, mb;
+  const int planes = n_pairs > 1 ? 3 : 1;
+  if (tc_make_maps(tc, &ma, P, p_plane, planes, V, N, ld, 64, 64, err, n)) return -2;      // A: MN-major (voxels contiguous), rows = cells
+  if (tc_make_maps(tc, &mb, Sx, s_plane, planes, Ke, N, Ke, 64, 64, err, n)) return -2;    // B: MN-major (genes contiguous), rows = cells
   auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
   const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, ma, ma, ma, N, tc_kps(N, splits), tm, tn, splits, kPolicyEvictNormal, kPolicyEvictNormal, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], N, tc_kps(N, splits), tm, tn,
+                                                                         splits, kPolicyEvictNormal, kPolicyEvictNormal, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
 
 // rpart[(z * ntiles_n + tn)][i] = sum over the tile's genes of (P dY_ext)_ik S_ext_ik
-static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, const __nv_bfloat16* dYb, const __nv_bfloat16* Sxb,
-                            float* rpart, int N, int V, int Ke, int ld, int splits, cudaStream_t s, char* err, size_t n) {
-  CUtensorMap ma, mb;
-  if (tc_make_map(tc, &ma, P, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
-  if (tc_make_map(tc, &mb, dYb, Ke, V, Ke, 64, 64, err, n)) return -2;   // B: MN-major (genes contiguous), rows = voxels
+static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* dYb, size_t dy_plane,
+                            int n_pairs, const __nv_bfloat16* Sxb, const float* Sxf, float* rpart, int N, int V, int Ke, int ld,
+                            int splits, cudaStream_t s, char* err, size_t n) {
+  TcMaps ma, mb;
+  const int planes = n_pairs > 1 ? 3 : 1;
+  if (tc_make_maps(tc, &ma, P, p_plane, planes, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
+  if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, 64, err, n)) return -2;  // B: MN-major (genes contiguous), rows = voxels
   auto kern = k_gemm_tc<true, false, TC_RDOT_BN, TC_RD_STAGES, 4, TcEpiRowDot>;
   const int smem = TC_RD_STAGES * (TC_BM + TC_RDOT_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
-  TcEpiRowDot epi{Sxb, Ke, rpart, N};
+  TcEpiRowDot epi{Sxb, Ke, rpart, N, Sxf};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, ma, ma, ma, V, tc_kps(V, splits), tm, tn, splits, kPolicyEvictNormal, kPolicyEvictLast, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], V, tc_kps(V, splits), tm, tn,
+                                                                         splits, kPolicyEvictNormal, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
-// dP = S_ext dY_ext^T fused with the softmax-Jacobian, Adam, and next iteration's P
-static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, const __nv_bfloat16* dYb, const TcAdamArgs& a,
-                              int N, int V, int Ke, cudaStream_t s, char* err, size_t n) {
-  CUtensorMap ma, mb;
-  if (tc_make_map(tc, &ma, Sxb, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
-  if (tc_make_map(tc, &mb, dYb, Ke, V, Ke, 64, TC_BWD_BN, err, n)) return -2; // B: K-major, rows = voxels
+// dP = S_ext dY_ext^T fused with the softmax-Jacobian, Adam, and (bf16 mode) next iteration's P
+static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_plane, const __nv_bfloat16* dYb, size_t dy_plane,
+                              int n_pairs, const TcAdamArgs& a, int N, int V, int Ke, cudaStream_t s, char* err, size_t n) {
+  TcMaps ma, mb;
+  const int planes = n_pairs > 1 ? 3 : 1;
+  if (tc_make_maps(tc, &ma, Sxb, s_plane, planes, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
+  if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN, err, n)) return -2; // B: K-major, rows = voxels
   // state arrays as fp32 2D tensors [N][V] (pitch ld): 32 x 32 boxes, 128B swizzle; stores clip at V / N
   CUtensorMap me[3];
   float* st[3] = {a.Mp, a.mp, a.vp};
@@ -844,7 +932,8 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, const __n
   if (tc_set_smem(kern, smem, err, n)) return -2;
   TcEpiAdam epi{a, N};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(V, TC_BWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, me[0], me[1], me[2], Ke, Ke, tm, tn, 1, kPolicyEvictNormal, kPolicyEvictLast, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, n_pairs, me[0], me[1], me[2], Ke, Ke, tm, tn, 1,
+                                                                              kPolicyEvictNormal, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 

@@ -29,11 +29,37 @@ __device__ __forceinline__ void store_p4<__nv_bfloat16>(__nv_bfloat16* dst, floa
   *reinterpret_cast<uint2*>(dst) = u;
 }
 
+// Three bf16 planes hi + mid + lo of an fp32 value (parity mode on tensor cores): x - (hi + mid + lo) ~ 2^-24 |x|.
+struct Split3 { __nv_bfloat16* base; size_t plane; };
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+__device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void store_split4(const Split3& d, size_t off, float a, float b, float c, float e) {
+  __nv_bfloat16 h[4], m[4], l[4];
+  split3(a, h[0], m[0], l[0]); split3(b, h[1], m[1], l[1]); split3(c, h[2], m[2], l[2]); split3(e, h[3], m[3], l[3]);
+  *reinterpret_cast<uint2*>(d.base + off) = make_uint2(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(d.base + d.plane + off) = make_uint2(pack_bf2(m[0], m[1]), pack_bf2(m[2], m[3]));
+  *reinterpret_cast<uint2*>(d.base + 2 * d.plane + off) = make_uint2(pack_bf2(l[0], l[1]), pack_bf2(l[2], l[3]));
+}
+// src (fp32, n elements, n % 4 == 0) -> three bf16 planes
+__global__ void k_split3(const float* __restrict__ src, Split3 dst, long long n4) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(src)[q];
+  store_split4(dst, (size_t)q * 4, v.x, v.y, v.z, v.w);
+}
+
 template <typename PT, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
 k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, int ldp,
                RowStat* __restrict__ stats, float* __restrict__ rowaux /* [N][2] or null */,
-               int want_entropy) {
+               int want_entropy, Split3 split /* base == null: none */) {
   __shared__ float sh[32];
   const int row = blockIdx.x;
   const float* mrow = M + (size_t)row * ldm;
@@ -101,7 +127,8 @@ k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, 
       if (c + 2 < V) h += p2 * ((v.z - mx) - st.log_z);
       if (c + 3 < V) h += p3 * ((v.w - mx) - st.log_z);
     }
-    store_p4<PT>(prow + c, p0, p1, p2, p3);
+    if (P != nullptr) store_p4<PT>(prow + c, p0, p1, p2, p3);
+    if (split.base != nullptr) store_split4(split, (size_t)row * ldp + c, p0, p1, p2, p3);
   };
   if (kCached) {
 #pragma unroll
@@ -421,7 +448,7 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
 // the spatial terms), density columns, cell-type columns.  Written in f32 and, for the
 // tensor-core path, bf16.
 __global__ void __launch_bounds__(kLossCols)
-k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ dYb) {
+k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ dYb, Split3 split) {
   const int k = blockIdx.x * kLossCols + threadIdx.x;
   const int j = blockIdx.y;
   if (k >= p.Ke) return;
@@ -460,6 +487,11 @@ k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ 
   }
   if (dY != nullptr) dY[o] = dy;
   if (dYb != nullptr) dYb[o] = __float2bfloat16_rn(dy);
+  if (split.base != nullptr) {
+    __nv_bfloat16 h, m, l;
+    split3(dy, h, m, l);
+    split.base[o] = h; split.base[split.plane + o] = m; split.base[2 * split.plane + o] = l;
+  }
 }
 
 // ------------------------------------------------------------------------------------

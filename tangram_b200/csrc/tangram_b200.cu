@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,7 +72,10 @@ struct tgb200_mapper {
   tgb200_config cfg;
   int N, V, K, T, Ke, ld;       // ld: leading dim of N x V arrays (elements)
   int ct_off;
-  bool bf16;
+  bool bf16;                    // throughput mode: bf16 operands
+  bool x3;                      // parity mode on tensor cores: three bf16 planes per operand, six partial products
+  bool tcm;                     // either tensor-core mode
+  int n_pairs = 1;
   // state
   DevBuf<float> M, m, v;        // N x ld
   int64_t step = 0;
@@ -155,7 +159,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   if (cfg->n_cells <= 0 || cfg->n_voxels <= 0 || cfg->n_genes <= 0 || cfg->n_types < 0)
     return fail(TGB200_ERR_INVALID, "bad shape cells=%d voxels=%d genes=%d types=%d", cfg->n_cells, cfg->n_voxels, cfg->n_genes, cfg->n_types);
   if (cfg->lambda_g1 == 0.f) return fail(TGB200_ERR_INVALID, "lambda_g1 cannot be 0.");  // mapping_utils.py:206-207
-  if (cfg->precision != TGB200_PREC_FP32 && cfg->precision != TGB200_PREC_BF16)
+  if (cfg->precision != TGB200_PREC_FP32 && cfg->precision != TGB200_PREC_BF16 && cfg->precision != TGB200_PREC_BF16X3)
     return fail(TGB200_ERR_INVALID, "unknown precision %d", cfg->precision);
   if (cfg->density_mode < 0 || cfg->density_mode > 2) return fail(TGB200_ERR_INVALID, "unknown density_mode %d", cfg->density_mode);
   if (cfg->lambda_ct_islands > 0.f && cfg->n_types <= 0) return fail(TGB200_ERR_INVALID, "lambda_ct_islands > 0 needs n_types > 0");
@@ -178,6 +182,9 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   if (h->cfg.adam_eps == 0.f) h->cfg.adam_eps = 1e-8f;
   h->N = cfg->n_cells; h->V = cfg->n_voxels; h->K = cfg->n_genes; h->T = cfg->n_types;
   h->bf16 = cfg->precision == TGB200_PREC_BF16;
+  h->x3 = cfg->precision == TGB200_PREC_BF16X3;
+  h->tcm = h->bf16 || h->x3;
+  h->n_pairs = h->x3 ? 6 : 1;
   h->ct_off = h->K + 2;
   h->Ke = (int)round_up(h->K + 2 + h->T, 64);
   h->ld = (int)round_up(h->V, 64);
@@ -194,6 +201,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     h->lseA = h->lse0.p; h->lseT = h->lse1.p;
   }
   if (h->bf16) { A(h->rowc.alloc(h->N)); A(h->Pb.alloc(nv)); A(h->Sxb.alloc((size_t)h->N * h->Ke)); A(h->dYb.alloc(vk)); }
+  else if (h->x3) { A(h->Pb.alloc(3 * nv)); A(h->Sxb.alloc((size_t)3 * h->N * h->Ke)); A(h->dYb.alloc(3 * vk)); }
   else A(h->Pf.alloc(nv));
   A(h->Sx.alloc((size_t)h->N * h->Ke));
   A(h->G.alloc(vk));
@@ -206,13 +214,15 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     const int max_s = (int)ceil_div(h->N, 512);
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
-    if (h->bf16) s = tc_forward_splits(h->N, h->V, h->Ke);
+    if (h->tcm) s = tc_forward_splits(h->N, h->V, h->Ke);
+    if (h->x3) { const int c = tc_splits_for_chain(h->N, 2048); if (c > s) s = c; }
     h->fwd_splits = s;
     if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
   }
   A(h->Y.alloc(vk + 4)); A(h->dY.alloc(vk));
-  h->rd_splits = h->bf16 ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
-  h->r_parts = (int)ceil_div(h->Ke, h->bf16 ? TC_RDOT_BN : SG_BN) * h->rd_splits;
+  h->rd_splits = h->tcm ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
+  if (h->x3) { const int c = tc_splits_for_chain(h->V, 2048); if (c > h->rd_splits) h->rd_splits = c; }
+  h->r_parts = (int)ceil_div(h->Ke, h->tcm ? TC_RDOT_BN : SG_BN) * h->rd_splits;
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
   // voxel rows per CTA of the loss reductions: enough CTAs for small V, bounded partial arrays for large V
@@ -237,7 +247,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     h->n_ct_blocks = (int)ceil_div((int64_t)h->V * h->T, 256);
     A(h->H.alloc((size_t)h->V * h->T)); A(h->ctpart.alloc(h->n_ct_blocks));
   }
-  if (st == TGB200_OK && h->bf16) st = tc_init(h->tc, g_err, sizeof(g_err));
+  if (st == TGB200_OK && h->tcm) st = tc_init(h->tc, g_err, sizeof(g_err));
   if (st != TGB200_OK) { delete h; return st; }
   CK(cudaDeviceSynchronize());
   *out = h;
@@ -266,8 +276,13 @@ static int upload_padded(tgb200_mapper* h, const float* src, int rows, int cols,
 }
 
 static int refresh_bf16_operands(tgb200_mapper* h, cudaStream_t s) {
-  if (!h->bf16) return TGB200_OK;
+  if (!h->tcm) return TGB200_OK;
   const long long n = (long long)h->N * h->Ke;
+  if (h->x3) {
+    k_split3<<<(unsigned)ceil_div(n / 4, 256), 256, 0, s>>>(h->Sx.p, Split3{h->Sxb.p, (size_t)n}, n / 4);
+    LAUNCH_CHECK("split3");
+    return TGB200_OK;
+  }
   k_f32_to_bf16<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(h->Sx.p, h->Sxb.p, n);
   LAUNCH_CHECK("f32_to_bf16");
   return TGB200_OK;
@@ -429,11 +444,12 @@ extern "C" int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void*
 
 // ---------------------------------------------------------------------------------------
 template <typename PT>
-static int launch_softmax_rows(tgb200_mapper* h, cudaStream_t s, PT* P, int want_entropy, float* rowaux) {
+static int launch_softmax_rows(tgb200_mapper* h, cudaStream_t s, PT* P, int want_entropy, float* rowaux,
+                               Split3 split = Split3{nullptr, 0}) {
   const int nvec = h->ld / 4;
   constexpr int TH = 256;
 #define SMX(ITEMS)                                                                                  \
-  k_softmax_rows<PT, TH, ITEMS><<<h->N, TH, 0, s>>>(h->M.p, h->ld, h->V, P, h->ld, h->stats.p, rowaux, want_entropy)
+  k_softmax_rows<PT, TH, ITEMS><<<h->N, TH, 0, s>>>(h->M.p, h->ld, h->V, P, h->ld, h->stats.p, rowaux, want_entropy, split)
   if (nvec <= TH * 1) SMX(1);
   else if (nvec <= TH * 2) SMX(2);
   else if (nvec <= TH * 4) SMX(4);
@@ -493,13 +509,18 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
     const long long nq = (long long)h->N * (h->Ke / 4);
     k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->Sx.p, h->inv_zt.p, h->N, h->Ke, h->Sxs.p);
     LAUNCH_CHECK("scale_rows");
+  } else if (h->x3) {
+    // parity mode on tensor cores: exact row pass every iteration, P written as three bf16 planes
+    CKS(launch_softmax_rows<float>(h, s, (float*)nullptr, want_entropy, rowaux, Split3{h->Pb.p, (size_t)h->N * h->ld}));
   } else {
     CKS(launch_softmax_rows<float>(h, s, h->Pf.p, want_entropy, rowaux));
   }
   const size_t vk = (size_t)h->V * h->Ke;
   float* out = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
-  if (h->bf16) {
-    CKS(tc_forward(h->tc, h->Pb.p, h->Sxs.p, out, h->N, h->V, h->Ke, h->ld, h->fwd_splits, s, g_err, sizeof(g_err)));
+  if (h->tcm) {
+    const __nv_bfloat16* sB = h->bf16 ? h->Sxs.p : h->Sxb.p;
+    CKS(tc_forward(h->tc, h->Pb.p, (size_t)h->N * h->ld, sB, (size_t)h->N * h->Ke, h->n_pairs, out, h->N, h->V, h->Ke, h->ld,
+                   h->fwd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_fwd");
   } else {
     GemmArgs g;
@@ -593,7 +614,8 @@ static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool re
   LAUNCH_CHECK("loss_scalars");
   dim3 dgrid(h->ncolchunk, h->V);
   // the tensor-core path consumes only the bf16 copy of dY_ext
-  k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->bf16 ? nullptr : h->dY.p, h->bf16 ? h->dYb.p : nullptr);
+  k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->tcm ? nullptr : h->dY.p, h->bf16 ? h->dYb.p : nullptr,
+                                            h->x3 ? Split3{h->dYb.p, (size_t)h->V * h->Ke} : Split3{nullptr, 0});
   LAUNCH_CHECK("dy_assemble");
   return TGB200_OK;
 }
@@ -624,8 +646,10 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   CKS(loss_stage(h, s, hist_row, !sharded));
 
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
-  if (h->bf16) {
-    CKS(tc_rowdot(h->tc, h->Pb.p, h->dYb.p, h->Sxb.p, h->rpart.p, h->N, h->V, h->Ke, h->ld, h->rd_splits, s, g_err, sizeof(g_err)));
+  const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
+  if (h->tcm) {
+    CKS(tc_rowdot(h->tc, h->Pb.p, nvp, h->dYb.p, vkp, h->n_pairs, h->Sxb.p, h->x3 ? h->Sx.p : nullptr, h->rpart.p, h->N, h->V,
+                  h->Ke, h->ld, h->rd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_rowdot");
   } else {
     GemmArgs g;
@@ -645,12 +669,17 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   LAUNCH_CHECK("rowdot_finalize");
   if (h->bf16) {
     TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, reinterpret_cast<const RowConst*>(h->rowc.p), h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
-                  h->Pb.p, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p};
-    CKS(tc_backward(h->tc, h->Sxb.p, h->dYb.p, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+                  nullptr, nullptr, h->Pb.p, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p};
+    CKS(tc_backward(h->tc, h->Sxb.p, nkp, h->dYb.p, vkp, 1, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_bwd_adam");
     // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
     float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
     h->p_state = 2;
+  } else if (h->x3) {
+    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, nullptr, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
+                  h->stats.p, h->rdot.p, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CKS(tc_backward(h->tc, h->Sxb.p, nkp, h->dYb.p, vkp, 6, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_bwd_adam");
   } else {
     GemmArgs g;
     g.A = h->Sx.p; g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
@@ -703,7 +732,7 @@ extern "C" int tgb200_get_mapping(tgb200_mapper* h, float* out, void* stream) {
   CK(cudaSetDevice(h->cfg.device));
   DevBuf<float> tmp;
   float* P = h->Pf.p;
-  if (h->bf16) { CKS(tmp.alloc((size_t)h->N * h->ld, false)); P = tmp.p; }
+  if (h->tcm) { CKS(tmp.alloc((size_t)h->N * h->ld, false)); P = tmp.p; }
   CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));      // :406-407
   CK(cudaMemcpy2DAsync(out, (size_t)h->V * sizeof(float), P, (size_t)h->ld * sizeof(float),
                        (size_t)h->V * sizeof(float), h->N, cudaMemcpyDefault, s));
@@ -746,7 +775,7 @@ extern "C" int tgb200_project(tgb200_mapper* h, const float* X, int64_t n_cols, 
   // softmax(M)^T X in fp32, gene columns streamed through in chunks (tangram/utils.py:368)
   DevBuf<float> Pt;
   float* P = h->Pf.p;
-  if (h->bf16) { CKS(Pt.alloc((size_t)h->N * h->ld, false)); P = Pt.p; }
+  if (h->tcm) { CKS(Pt.alloc((size_t)h->N * h->ld, false)); P = Pt.p; }
   CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));
   const int chunk = 2048;
   const int ldc = (int)round_up(n_cols < chunk ? n_cols : chunk, 4);
@@ -872,11 +901,16 @@ extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* ou
   if (nm == "Y") { src = h->Y.p; cnt = vk; }
   else if (nm == "dY") {
     src = h->dY.p; cnt = vk;
-    if (h->bf16 && out_host) {     // only the bf16 copy exists on the tensor-core path
-      std::vector<__nv_bfloat16> tmp((size_t)vk);
+    if (h->tcm && out_host) {     // only the bf16 copy (or its three planes) exists on the tensor-core paths
+      const int planes = h->x3 ? 3 : 1;
+      std::vector<__nv_bfloat16> tmp((size_t)vk * planes);
       if (cap < cnt) return fail(TGB200_ERR_INVALID, "buffer 'dY' needs %lld floats", (long long)cnt);
-      CK(cudaMemcpy(tmp.data(), h->dYb.p, (size_t)vk * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
-      for (int64_t i = 0; i < vk; ++i) out_host[i] = __bfloat162float(tmp[(size_t)i]);
+      CK(cudaMemcpy(tmp.data(), h->dYb.p, (size_t)vk * planes * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < vk; ++i) {
+        float acc = 0.f;
+        for (int pl = planes - 1; pl >= 0; --pl) acc += __bfloat162float(tmp[(size_t)pl * vk + (size_t)i]);
+        out_host[i] = acc;
+      }
       *n = cnt;
       return TGB200_OK;
     }

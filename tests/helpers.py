@@ -53,3 +53,10 @@ def assert_same_print(ours, ref):
     for (_, va), (_, vb) in zip(a, b):
         va, vb = float(va), float(vb)
         assert abs(va - vb) <= 0.0011 + 1e-6 * abs(vb), (ours, ref)
+
+
+def traj_err(a, b):
+    """Error of a loss trajectory that crosses zero: |a - b| relative to max(|b|, a quarter of the trajectory's scale)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.25 * np.max(np.abs(b)))))

@@ -45,11 +45,12 @@ def test_oracle_reproduces_reference_known_answers(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("case", CASES)
-def test_cuda_reproduces_reference_known_answers(case):
+def test_cuda_reproduces_reference_known_answers(case, precision):
     from tangram_b200 import Mapper
     kw, e = _inputs(case)
-    out, hist = Mapper(device="cuda:0", **kw).train(500, print_each=None)
+    out, hist = Mapper(device="cuda:0", precision=precision, **kw).train(500, print_each=None)
     _check(out[0, 0], e)
 
 
