@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("TGB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("TGB200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("TGB200_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -288,9 +288,9 @@ def main():
         step_ms = sum(avg.values())
         top = max(avg, key=avg.get)
         Nl = r1 - r0
-        sS = 2.0 if a.precision == "bf16" else 4.0
+        sS = 2.0 if a.precision == "bf16" else (6.0 if a.precision == "bf16x3" else 4.0)
         # algorithmic work of each kernel: flops, HBM bytes per launch
-        pb = 2.0 if a.precision == "bf16" else 4.0          # bytes per element of the stored P
+        pb = {"bf16": 2.0, "bf16x3": 6.0}.get(a.precision, 4.0)          # bytes per element of the stored P
         work = {
             "gemm_fwd": (2.0 * Nl * V * K, pb * Nl * V + sS * Nl * K + 4.0 * V * K),
             "gemm_rowdot": (2.0 * Nl * V * K, pb * Nl * V + sS * Nl * K + sS * V * K),
@@ -306,11 +306,12 @@ def main():
         if key:
             fl, by = work[key]
             t_s = avg[top] / 1e3
-            tf_peak = pk["tf_sust"] if a.precision == "bf16" else 74.0   # fp32 FFMA: 148 SM x 128 lanes x 2 x 1.965 GHz
+            # bf16x3 issues 6 bf16 MMAs per useful product; fp32 FFMA peak: 148 SM x 128 lanes x 2 x 1.965 GHz
+            tf_peak = pk["tf_sust"] if a.precision == "bf16" else (pk["tf_sust"] / 6.0 if a.precision == "bf16x3" else 74.0)
             t_fl = fl / (tf_peak * 1e12) if fl else 0.0
             t_by = by / (pk["hbm"] * 1e9)
             if t_fl >= t_by:
-                roof = {"bound": "tensor" if a.precision == "bf16" else "fp32-ffma", "achieved": fl / t_s / 1e12,
+                roof = {"bound": "tensor" if a.precision != "fp32" else "fp32-ffma", "achieved": fl / t_s / 1e12,
                         "peak": tf_peak, "unit": "TFLOP/s"}
             else:
                 roof = {"bound": "hbm", "achieved": by / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
@@ -321,13 +322,13 @@ def main():
             others = {}
             for kname, ms in avg.items():
                 kk = next((k for k in ("gemm_fwd", "gemm_rowdot", "gemm_bwd_adam") if k in kname), None)
-                if kk and a.precision == "bf16":
+                if kk and a.precision != "fp32":
                     others[kname] = {"tflops": work[kk][0] / (ms / 1e3) / 1e12,
                                      "frac_of_sustained_bf16_peak": work[kk][0] / (ms / 1e3) / 1e12 / pk["tf_sust"],
                                      "hbm_GBs": work[kk][1] / (ms / 1e3) / 1e9}
             roof["contractions"] = others
         hb, fl_it = eng.algorithmic_cost()
-        roof_step = max(hb / (pk["hbm"] * 1e9), fl_it / ((pk["tf_sust"] if a.precision == "bf16" else 74.0) * 1e12))
+        roof_step = max(hb / (pk["hbm"] * 1e9), fl_it / ({"bf16": pk["tf_sust"], "bf16x3": pk["tf_sust"] / 6.0}.get(a.precision, 74.0) * 1e12))
         if roof is not None:
             roof["step_roofline_frac"] = roof_step / (elapsed / a.steps)
             roof["mts_tflops"] = 2.0 * Nl * V * K / (avg.get(next((k for k in avg if "gemm_fwd" in k), top), 1e9) / 1e3) / 1e12
@@ -374,7 +375,7 @@ def main():
         line = {"metric": metric, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": elapsed / a.steps * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None,
-                "dtype": "bf16 operands / f32 accumulate+state" if a.precision == "bf16" else "f32",
+                "dtype": {"bf16": "bf16 operands / f32 accumulate+state", "bf16x3": "f32 via 3xbf16 split operands on tensor cores / f32 accumulate+state"}.get(a.precision, "f32"),
                 "data": "synthetic", "config": dict(config, precision=a.precision,
                                                     l2="L2 flushed between timed iterations" if flush else "state exceeds L2 (no flush)"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}

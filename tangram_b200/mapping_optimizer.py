@@ -6,7 +6,9 @@ same return types and history conventions.  There is no CPU path: `device` must 
 CUDA device with compute capability 10.x.
 
 Additions (keyword-only, all optional):
-  precision   "fp32" (parity mode, default) | "bf16" (tcgen05 tensor cores)
+  precision   "bf16x3" (default: parity-grade fp32 results on tcgen05 tensor cores -- every operand is split into three
+              bf16 planes and the six significant partial products are accumulated in fp32) |
+              "fp32" (FFMA contractions, the cross-check) | "bf16" (plain bf16 operands: throughput mode)
   M0          explicit initial mapping (ndarray N x V); default is the reference draw
   process_group / shard  cell-sharded multi-GPU operation (one process per GPU): every rank passes the
               full S / M0 and keeps rows shard_rows(N, rank, world)
@@ -109,7 +111,7 @@ class Mapper:
         adata_map=None,
         random_state=None,
         *,
-        precision="fp32",
+        precision="bf16x3",
         M0=None,
         process_group=None,
         shard=None,
