@@ -76,6 +76,8 @@ enum {
   TGB200_HIST_NEIGHBORHOOD = 7, /* gv_neighborhood_sim :237  */
   TGB200_HIST_CT_ISLANDS = 8,   /* ct_island_penalty   :246  */
   TGB200_HIST_GETIS_ORD = 9,    /* getis_ord_sim       :257  */
+  TGB200_HIST_COUNT = 10,       /* count_reg     (MapperConstrained :543) */
+  TGB200_HIST_F_REG = 11,       /* lambda_f_reg  (MapperConstrained :544) */
   TGB200_HIST_COLS = 16
 };
 
@@ -102,6 +104,11 @@ typedef struct tgb200_config {
   float adam_beta1;        /* torch.optim.Adam defaults used at :373 -> 0.9   */
   float adam_beta2;        /* 0.999 */
   float adam_eps;          /* 1e-8  */
+  /* MapperConstrained (mapping_optimizer.py:411-639): a per-cell sigmoid filter F is learned next to M */
+  int32_t constrained;     /* 1 = constrained mode (then density_mode must be NONE or CELLS) */
+  float lambda_count;      /* :426 */
+  float lambda_f_reg;      /* :427 */
+  float target_count;      /* :428, :480-483 */
 } tgb200_config;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -129,6 +136,12 @@ TGB200_API int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indp
 TGB200_API int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* stream);
 /* Device-side N(0,1) init (Philox) for throughput runs; NOT bit-compatible with :150. */
 TGB200_API int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream);
+
+/* Constrained mode: initial filter logits F0 (n_cells, host or device; the reference draws them at :490).
+ * Resets the filter's Adam state. */
+TGB200_API int tgb200_set_filter(tgb200_mapper* h, const float* F0, void* stream);
+/* Filter logits F and/or sigmoid(F) (n_cells each, host or device; NULL to skip).  Replaces :638. */
+TGB200_API int tgb200_get_filter(tgb200_mapper* h, float* F_out, float* f_out, void* stream);
 
 /* ---- the hot loop ------------------------------------------------------------------ */
 

@@ -398,3 +398,129 @@ def spatial_weights_from_graph(conn, dist, standardized, self_inclusion):
     if self_inclusion:
         w = w + sp.identity(w.shape[0], format="csr")
     return w.tocsr().astype(np.float32)
+
+
+class OracleMapperConstrained:
+    """Closed-form CPU restatement of reference `MapperConstrained` (mapping_optimizer.py:411-639): the mapping
+    matrix M plus a per-cell filter F (sigmoid), Adam over [M, F].  TEST INFRASTRUCTURE ONLY.
+
+    Quirks preserved: M is drawn twice and the second draw is used (:475, :485); F is drawn after M (:490);
+    `entropy_reg` is logged as +sum(P log P) (:526, :540); history values are strings (:630)."""
+
+    def __init__(self, S, G, d, lambda_d=1, lambda_g1=1, lambda_g2=1, lambda_r=0, lambda_count=1, lambda_f_reg=1,
+                 target_count=None, device="cpu", adata_map=None, random_state=None, dtype=torch.float32,
+                 M0=None, F0=None):
+        if adata_map is not None:
+            raise NotImplementedError
+        self.dtype = dtype
+        self.S = torch.as_tensor(np.asarray(S), dtype=torch.float32).to(dtype)
+        self.G = torch.as_tensor(np.asarray(G), dtype=torch.float32).to(dtype)
+        self.d = None if d is None else torch.as_tensor(np.asarray(d), dtype=torch.float32).to(dtype)
+        self.lam = dict(d=lambda_d, g1=lambda_g1, g2=lambda_g2, r=lambda_r, c=lambda_count, f=lambda_f_reg)
+        self.target_count = self.G.shape[0] if target_count is None else target_count
+        N, V = self.S.shape[0], self.G.shape[0]
+        if M0 is None or F0 is None:
+            if random_state:
+                np.random.seed(seed=random_state)
+            np.random.normal(0, 1, (N, V))          # first draw, discarded by the reference (:475 then :485)
+            M0 = np.random.normal(0, 1, (N, V))
+            F0 = np.random.normal(0, 1, N)
+        self.M = torch.as_tensor(np.asarray(M0), dtype=torch.float32).to(dtype).clone()
+        self.F = torch.as_tensor(np.asarray(F0), dtype=torch.float32).to(dtype).clone()
+        self.mM, self.vM = torch.zeros_like(self.M), torch.zeros_like(self.M)
+        self.mF, self.vF = torch.zeros_like(self.F), torch.zeros_like(self.F)
+        self.t = 0
+
+    def loss_and_grad(self):
+        lam, S, G = self.lam, self.S, self.G
+        N, V = self.M.shape
+        K = S.shape[1]
+        P = torch.softmax(self.M, dim=1)                       # :506
+        f = torch.sigmoid(self.F)                              # :507
+        Sf = S * f[:, None]                                    # :519
+        Y = P.t() @ Sf                                         # :521
+        terms = {}
+        c_g, nyg, ngg = _cos_cols(Y, G)
+        c_v, nyv, ngv = _cos_cols(Y.t(), G.t())
+        gv, vg = lam["g1"] * c_g.mean(), lam["g2"] * c_v.mean()
+        terms["main_loss"] = float(c_g.mean())
+        terms["vg_reg"] = float(c_v.mean()) if lam["g2"] != 0 else float("nan")
+        dY = -lam["g1"] * _dcos_cols(Y, G, c_g, nyg, ngg)
+        if lam["g2"] != 0:
+            dY = dY - lam["g2"] * _dcos_cols(Y.t(), G.t(), c_v, nyv, ngv).t()
+        total = -gv - vg
+        s = f.sum()
+        df_extra = torch.zeros_like(f)
+        dP_cols = None
+        if self.d is not None:                                 # :511-515
+            csf = (P * f[:, None]).sum(dim=0)
+            dhat = csf / s
+            kl = (torch.special.xlogy(self.d, self.d) - self.d * torch.log(dhat)).sum()
+            total = total + lam["d"] * kl
+            terms["kl_reg"] = float(kl) if lam["d"] != 0 else float("nan")
+            g_cs = -lam["d"] * self.d / csf                    # dL / d csf_j
+            dP_cols = g_cs                                     # times f_i below
+            df_extra = df_extra + (P @ g_cs) + lam["d"] * self.d.sum() / s
+        else:
+            terms["kl_reg"] = float("nan")
+        plogp = (torch.log_softmax(self.M, dim=1) * P).sum()
+        total = total - lam["r"] * plogp                       # :526, :575
+        terms["entropy_reg"] = float(plogp) if lam["r"] != 0 else float("nan")
+        cnt = s - self.target_count                            # :528-529
+        total = total + lam["c"] * cnt.abs()
+        terms["count_reg"] = float(cnt.abs()) if lam["c"] != 0 else float("nan")
+        freg = (f - f * f).sum()                               # :531-532
+        total = total + lam["f"] * freg
+        terms["lambda_f_reg"] = float(freg) if lam["f"] != 0 else float("nan")
+        terms["total_loss"] = float(total)
+        # backward
+        SdY = S @ dY.t()                                       # (N, V): d Y-terms / d (f_i P_ij)
+        dP = f[:, None] * SdY
+        if dP_cols is not None:
+            dP = dP + f[:, None] * dP_cols[None, :]
+        if lam["r"] != 0:
+            dP = dP - lam["r"] * (torch.log_softmax(self.M, dim=1) + 1.0)
+        dM = P * (dP - (P * dP).sum(dim=1, keepdim=True))
+        df = (P * SdY).sum(dim=1) + df_extra + lam["c"] * torch.sign(cnt) + lam["f"] * (1 - 2 * f)
+        dF = df * f * (1 - f)
+        return terms, dM, dF
+
+    def _adam(self, x, g, m, v, lr, b1=0.9, b2=0.999, eps=1e-8):
+        m = m + (g - m) * (1 - b1)
+        v = v * b2 + (1 - b2) * g * g
+        step = lr / (1 - b1 ** self.t)
+        x = x - step * (m / (v.sqrt() / ((1 - b2 ** self.t) ** 0.5) + eps))
+        return x, m, v
+
+    def train(self, num_epochs, learning_rate=0.1, print_each=100):
+        keys = ["total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg", "count_reg", "lambda_f_reg"]
+        hist = {k: [] for k in keys}
+        self.float_history = {k: [] for k in keys}
+        for t in range(num_epochs):
+            terms, dM, dF = self.loss_and_grad()
+            for k in keys:
+                self.float_history[k].append(terms[k])
+                hist[k].append(format_constrained_value(k, terms[k]))
+            if print_each is not None and t % print_each == 0:
+                print(format_constrained_terms(terms))
+            self.t += 1
+            self.M, self.mM, self.vM = self._adam(self.M, dM, self.mM, self.vM, learning_rate)
+            self.F, self.mF, self.vF = self._adam(self.F, dF, self.mF, self.vF, learning_rate)
+        out = torch.softmax(self.M, dim=1).to(torch.float32).numpy()
+        return out, torch.sigmoid(self.F).to(torch.float32).numpy(), hist
+
+
+def format_constrained_value(key, x):
+    """History entries of MapperConstrained are `str(...)` of what _loss_fn returns (:630): a tensor repr for
+    total_loss, python floats (or nan) for the rest."""
+    if key == "total_loss":
+        return "tensor({:.4f}, grad_fn=<AddBackward0>)".format(x)
+    return str(x)
+
+
+def format_constrained_terms(terms):
+    """The print line of MapperConstrained (:546-573)."""
+    names = [("main_loss", "Score"), ("vg_reg", "VG reg"), ("kl_reg", "KL reg"), ("entropy_reg", "Entropy reg"),
+             ("count_reg", "Count reg"), ("lambda_f_reg", "Lambda f reg")]
+    msg = ["{}: {:.3f}".format(n, terms[k]) for k, n in names if not np.isnan(terms[k])]
+    return str(msg).replace("[", "").replace("]", "").replace("'", "")

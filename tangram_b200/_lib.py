@@ -25,6 +25,8 @@ class Config(ctypes.Structure):
         ("lambda_neighborhood_g1", ctypes.c_float), ("lambda_ct_islands", ctypes.c_float),
         ("lambda_getis_ord", ctypes.c_float),
         ("adam_beta1", ctypes.c_float), ("adam_beta2", ctypes.c_float), ("adam_eps", ctypes.c_float),
+        ("constrained", ctypes.c_int32), ("lambda_count", ctypes.c_float), ("lambda_f_reg", ctypes.c_float),
+        ("target_count", ctypes.c_float),
     ]
 
 
@@ -47,6 +49,8 @@ SIGNATURES = {
     "tgb200_set_graph": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, ctypes.c_int64, _P]),
     "tgb200_set_mapping": (ctypes.c_int, [_P, _P, _P]),
     "tgb200_init_mapping_normal": (ctypes.c_int, [_P, ctypes.c_uint64, _P]),
+    "tgb200_set_filter": (ctypes.c_int, [_P, _P, _P]),
+    "tgb200_get_filter": (ctypes.c_int, [_P, _P, _P, _P]),
     "tgb200_run": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_float, _P]),
     "tgb200_step_begin": (ctypes.c_int, [_P, _P]),
     "tgb200_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), _I64]),

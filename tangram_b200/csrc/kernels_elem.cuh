@@ -154,19 +154,65 @@ k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, 
 
 // Sum of per-row scalars (entropy, L1, L2) over this rank's rows -> 4-float tail of the
 // exchange buffer.  Deterministic (fixed tree), one CTA.
+// tail (8 floats): [0] sum_i h_i, [1] sum|M|, [2] sum M^2, [3] sum_i f_i, [4] sum_i (f_i - f_i^2)  (f: constrained mode)
+constexpr int kTail = 8;
 __global__ void __launch_bounds__(1024)
-k_row_scalar_reduce(const RowStat* __restrict__ stats, const float* __restrict__ rowaux, int n_rows,
-                    float* __restrict__ tail) {
+k_row_scalar_reduce(const RowStat* __restrict__ stats, const float* __restrict__ rowaux, const float* __restrict__ f,
+                    int n_rows, float* __restrict__ tail) {
   __shared__ float sh[32];
-  float h = 0.f, a = 0.f, b = 0.f;
+  float h = 0.f, a = 0.f, b = 0.f, fs = 0.f, fr = 0.f;
   for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
-    h += stats[i].h;
+    if (stats) h += stats[i].h;
     if (rowaux) { a += rowaux[2 * i]; b += rowaux[2 * i + 1]; }
+    if (f) { const float x = f[i]; fs += x; fr += x - x * x; }
   }
   h = block_reduce<false>(h, sh);
   a = block_reduce<false>(a, sh);
   b = block_reduce<false>(b, sh);
-  if (threadIdx.x == 0) { tail[0] = h; tail[1] = a; tail[2] = b; tail[3] = 0.f; }
+  fs = block_reduce<false>(fs, sh);
+  fr = block_reduce<false>(fr, sh);
+  if (threadIdx.x == 0) {
+    tail[0] = h; tail[1] = a; tail[2] = b; tail[3] = fs; tail[4] = fr; tail[5] = 0.f; tail[6] = 0.f; tail[7] = 0.f;
+  }
+}
+
+// ---- constrained mode (MapperConstrained, mapping_optimizer.py:411-639): per-cell filter f = sigmoid(F) ----------
+// S_f = f o S_ext is the operand of all three contractions (:519, :521); its "ones" column becomes f, so the
+// filtered column sums (:513) come out of the forward GEMM like the plain ones do.
+__global__ void k_filter_prepare(const float* __restrict__ F, const float* __restrict__ Sx, int n_rows, int Ke,
+                                 float* __restrict__ f, float* __restrict__ Sf) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of S_ext each
+  const int nvec = Ke >> 2;
+  if (q >= (long long)n_rows * nvec) return;
+  const int r = (int)(q / nvec);
+  const float fi = 1.f / (1.f + expf(-F[r]));
+  if ((int)(q % nvec) == 0) f[r] = fi;
+  float4 v = reinterpret_cast<const float4*>(Sx)[q];
+  v.x *= fi; v.y *= fi; v.z *= fi; v.w *= fi;
+  reinterpret_cast<float4*>(Sf)[q] = v;
+}
+// dL/df_i = r_i / f_i (the row-dot of the contractions: Y is linear in f_i) + density/count/regulariser parts;
+// dL/dF_i = dL/df_i f_i (1 - f_i); Adam on F with the same scalars as M (one optimizer over [M, F], :607).
+// fscal: [0] lambda_d * sum(d) / sum(f)   [1] sign(sum(f) - target_count)
+struct AdamScalarsF { float one_minus_beta1, beta2, one_minus_beta2, step_size, bc2_sqrt, eps; };
+__global__ void k_filter_update(int n_rows, const float* __restrict__ rdot, const float* __restrict__ f,
+                                const float* __restrict__ fscal, float lam_c, float lam_f, AdamScalarsF a,
+                                float* __restrict__ F, float* __restrict__ mF, float* __restrict__ vF) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const float fi = f[i];
+  const float df = rdot[i] / fi + fscal[0] + lam_c * fscal[1] + lam_f * (1.f - 2.f * fi);
+  const float g = df * fi * (1.f - fi);
+  float m = mF[i], v = vF[i];
+  m = m + (g - m) * a.one_minus_beta1;
+  v = v * a.beta2 + a.one_minus_beta2 * g * g;
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  F[i] = F[i] - a.step_size * (m / denom);
+  mF[i] = m; vF[i] = v;
+}
+__global__ void k_sigmoid(const float* __restrict__ F, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.f / (1.f + expf(-F[i]));
 }
 
 // ------------------------------------------------------------------------------------
@@ -209,6 +255,10 @@ struct LossParams {
   float* coefAg; float* coefBg;   // Ke
   float* coefAr; float* coefBr;   // V
   float* densg;                   // V
+  // constrained mode
+  int constrained;
+  float lam_c, lam_f, target_count;
+  float* fscal;                   // [2] coefficients for k_filter_update
 };
 
 // Y = sum over split partials; per-gene <Y,G>, |Y|^2, colsum(Y) for this row chunk;
@@ -400,16 +450,21 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
   }
 
   // density KL (:212-221): KLDivLoss(sum)(log dhat, d) = sum xlogy(d,d) - d log dhat
-  float kl = 0.f;
+  float kl = 0.f, dsum = 0.f;
+  const float* tailp = p.Y + (size_t)p.V * p.Ke;
+  const float fsum = tailp[3];                       // sum_i f_i (constrained mode)
   if (p.density_mode != 0) {
     for (int j = tid; j < p.V; j += nt) {
       const float cs = p.Y[(size_t)j * p.Ke + p.K] + p.Y[(size_t)j * p.Ke + p.K + 1];
-      const float dhat = (p.density_mode == 1) ? cs / (float)p.n_cells_global : cs;
+      float dhat = (p.density_mode == 1) ? cs / (float)p.n_cells_global : cs;
+      if (p.constrained) dhat = cs / fsum;           // :512-514  (f-weighted column sums / sum f)
       const float dj = p.d[j];
       kl += ((dj > 0.f) ? dj * logf(dj) : 0.f) - dj * logf(dhat);
+      dsum += dj;
       p.densg[j] = -p.lam_d * dj / cs;
     }
     kl = block_reduce<false>(kl, sh);
+    dsum = block_reduce<false>(dsum, sh);
   }
 
   float ct = 0.f;
@@ -430,6 +485,15 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
     if (p.lam_ct > 0.f) total += p.lam_ct * ct;
     if (p.lam_nb > 0.f) total -= p.lam_nb * nb;
     if (p.lam_go > 0.f) total -= p.lam_go * go;
+    float count_abs = 0.f, freg = 0.f;
+    if (p.constrained) {                               // :528-532, :575
+      const float cnt = fsum - p.target_count;
+      count_abs = fabsf(cnt);
+      freg = tail[4];
+      total += p.lam_c * count_abs + p.lam_f * freg;
+      p.fscal[0] = (p.density_mode != 0) ? p.lam_d * dsum / fsum : 0.f;
+      p.fscal[1] = (float)((cnt > 0.f) - (cnt < 0.f));
+    }
     hist_row[0] = total;
     hist_row[1] = gv;
     hist_row[2] = (p.lam_g2 != 0.f) ? vg : nan;
@@ -440,7 +504,9 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
     hist_row[7] = (p.lam_nb > 0.f) ? nb : nan;
     hist_row[8] = (p.lam_ct > 0.f) ? ct : nan;
     hist_row[9] = (p.lam_go > 0.f) ? go : nan;
-    for (int i = 10; i < 16; ++i) hist_row[i] = 0.f;
+    hist_row[10] = (p.constrained && p.lam_c != 0.f) ? count_abs : nan;
+    hist_row[11] = (p.constrained && p.lam_f != 0.f) ? freg : nan;
+    for (int i = 12; i < 16; ++i) hist_row[i] = 0.f;
   }
 }
 

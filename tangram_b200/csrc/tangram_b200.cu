@@ -95,12 +95,15 @@ struct tgb200_mapper {
   float* lseA = nullptr;        // offset the current Pb was produced with
   float* lseT = nullptr;        // exact log-sum-exp of the current rows
   int z_parts = 0;
+  // constrained mode (MapperConstrained): filter logits, their Adam state, f = sigmoid(F), S_f = f o S_ext
+  bool constrained = false, have_filter = false;
+  DevBuf<float> Fl, mF, vF, fsig, Sf, fscal;
   int p_state = 0;              // 0: Pb invalid, 1: fresh from the row pass (normalised), 2: written by backward
   int r_parts = 0, rd_splits = 1;
   // forward / loss
   int fwd_splits = 1;
   DevBuf<float> Ypart;          // splits x V x Ke (only when splits > 1)
-  DevBuf<float> Y;              // V x Ke + 4 (exchange buffer)
+  DevBuf<float> Y;              // V x Ke + kTail (exchange buffer)
   DevBuf<float> dY;             // V x Ke
   DevBuf<__nv_bfloat16> dYb;
   DevBuf<float> ngc, ngr, WG, nwg, AG, nag, sgnG, Z, Zg, H;
@@ -142,6 +145,9 @@ static void mark(tgb200_mapper* h, cudaStream_t s, const char* name) {
     mark(h, s, name);                                                                       \
   } while (0)
 
+// the fp32 S_ext every contraction consumes: f o S_ext in constrained mode, S_ext otherwise
+static float* s_act(tgb200_mapper* h) { return h->constrained ? h->Sf.p : h->Sx.p; }
+
 static bool needs_rowaux(const tgb200_config& c) { return c.lambda_l1 != 0.f || c.lambda_l2 != 0.f; }
 static bool needs_rowscalars(const tgb200_config& c) {
   return c.lambda_r != 0.f || c.lambda_l1 != 0.f || c.lambda_l2 != 0.f;
@@ -163,6 +169,12 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     return fail(TGB200_ERR_INVALID, "unknown precision %d", cfg->precision);
   if (cfg->density_mode < 0 || cfg->density_mode > 2) return fail(TGB200_ERR_INVALID, "unknown density_mode %d", cfg->density_mode);
   if (cfg->lambda_ct_islands > 0.f && cfg->n_types <= 0) return fail(TGB200_ERR_INVALID, "lambda_ct_islands > 0 needs n_types > 0");
+  if (cfg->constrained) {
+    if (cfg->density_mode == TGB200_DENSITY_SOURCE) return fail(TGB200_ERR_INVALID, "constrained mode has no d_source (mapping_optimizer.py:417-432)");
+    if (cfg->lambda_neighborhood_g1 > 0.f || cfg->lambda_ct_islands > 0.f || cfg->lambda_getis_ord > 0.f || cfg->lambda_l1 != 0.f || cfg->lambda_l2 != 0.f)
+      return fail(TGB200_ERR_INVALID, "constrained mode has no spatial / L1 / L2 terms (mapping_optimizer.py:417-432)");
+    if (cfg->n_cells_global > 0 && cfg->n_cells_global != cfg->n_cells && cfg->target_count <= 0.f) return fail(TGB200_ERR_INVALID, "target_count must be given");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -181,6 +193,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   if (h->cfg.adam_beta2 == 0.f) h->cfg.adam_beta2 = 0.999f;
   if (h->cfg.adam_eps == 0.f) h->cfg.adam_eps = 1e-8f;
   h->N = cfg->n_cells; h->V = cfg->n_voxels; h->K = cfg->n_genes; h->T = cfg->n_types;
+  h->constrained = cfg->constrained != 0;
   h->bf16 = cfg->precision == TGB200_PREC_BF16;
   h->x3 = cfg->precision == TGB200_PREC_BF16X3;
   h->tcm = h->bf16 || h->x3;
@@ -219,7 +232,11 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     h->fwd_splits = s;
     if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
   }
-  A(h->Y.alloc(vk + 4)); A(h->dY.alloc(vk));
+  A(h->Y.alloc(vk + kTail)); A(h->dY.alloc(vk));
+  if (h->constrained) {
+    A(h->Fl.alloc(h->N)); A(h->mF.alloc(h->N)); A(h->vF.alloc(h->N)); A(h->fsig.alloc(h->N));
+    A(h->Sf.alloc((size_t)h->N * h->Ke)); A(h->fscal.alloc(4));
+  }
   h->rd_splits = h->tcm ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
   if (h->x3) { const int c = tc_splits_for_chain(h->V, 2048); if (c > h->rd_splits) h->rd_splits = c; }
   h->r_parts = (int)ceil_div(h->Ke, h->tcm ? TC_RDOT_BN : SG_BN) * h->rd_splits;
@@ -279,11 +296,11 @@ static int refresh_bf16_operands(tgb200_mapper* h, cudaStream_t s) {
   if (!h->tcm) return TGB200_OK;
   const long long n = (long long)h->N * h->Ke;
   if (h->x3) {
-    k_split3<<<(unsigned)ceil_div(n / 4, 256), 256, 0, s>>>(h->Sx.p, Split3{h->Sxb.p, (size_t)n}, n / 4);
+    k_split3<<<(unsigned)ceil_div(n / 4, 256), 256, 0, s>>>(s_act(h), Split3{h->Sxb.p, (size_t)n}, n / 4);
     LAUNCH_CHECK("split3");
     return TGB200_OK;
   }
-  k_f32_to_bf16<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(h->Sx.p, h->Sxb.p, n);
+  k_f32_to_bf16<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(s_act(h), h->Sxb.p, n);
   LAUNCH_CHECK("f32_to_bf16");
   return TGB200_OK;
 }
@@ -430,6 +447,34 @@ extern "C" int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* strea
   return TGB200_OK;
 }
 
+extern "C" int tgb200_set_filter(tgb200_mapper* h, const float* F0, void* stream) {
+  if (!h || !F0) return fail(TGB200_ERR_INVALID, "null argument");
+  if (!h->constrained) return fail(TGB200_ERR_INVALID, "handle was not created in constrained mode");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->Fl.p, F0, h->N * sizeof(float), cudaMemcpyDefault, s));
+  CK(cudaMemsetAsync(h->mF.p, 0, h->N * sizeof(float), s));
+  CK(cudaMemsetAsync(h->vF.p, 0, h->N * sizeof(float), s));
+  h->have_filter = true;
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_get_filter(tgb200_mapper* h, float* F_out, float* f_out, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (!h->constrained || !h->have_filter) return fail(TGB200_ERR_STATE, "no filter on this handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  if (F_out) CK(cudaMemcpyAsync(F_out, h->Fl.p, h->N * sizeof(float), cudaMemcpyDefault, s));
+  if (f_out) {
+    k_sigmoid<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->Fl.p, h->N, h->fsig.p);     // :638
+    LAUNCH_CHECK("sigmoid");
+    CK(cudaMemcpyAsync(f_out, h->fsig.p, h->N * sizeof(float), cudaMemcpyDefault, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   cudaStream_t s = (cudaStream_t)stream;
@@ -479,6 +524,8 @@ static LossParams make_loss_params(tgb200_mapper* h) {
   p.coefA = h->coefA.p; p.coefB = h->coefB.p; p.coefAn = h->coefAn.p; p.coefBn = h->coefBn.p;
   p.coefAg = h->coefAg.p; p.coefBg = h->coefBg.p; p.coefAr = h->coefAr.p; p.coefBr = h->coefBr.p;
   p.densg = h->densg.p;
+  p.constrained = h->constrained ? 1 : 0;
+  p.lam_c = c.lambda_count; p.lam_f = c.lambda_f_reg; p.target_count = c.target_count; p.fscal = h->fscal.p;
   return p;
 }
 
@@ -490,6 +537,7 @@ static int check_ready(tgb200_mapper* h) {
   if (c.lambda_ct_islands > 0.f && (!h->have_ct || !h->F.set)) return fail(TGB200_ERR_STATE, "lambda_ct_islands > 0 needs ct_encode and the neighborhood_filter graph");
   if (c.lambda_neighborhood_g1 > 0.f && !h->W.set) return fail(TGB200_ERR_STATE, "lambda_neighborhood_g1 > 0 needs the voxel_weights graph");
   if (c.lambda_getis_ord > 0.f && !h->A.set) return fail(TGB200_ERR_STATE, "lambda_getis_ord > 0 needs the spatial_weights graph");
+  if (h->constrained && !h->have_filter) return fail(TGB200_ERR_STATE, "constrained mode: call tgb200_set_filter first");
   return TGB200_OK;
 }
 
@@ -507,7 +555,7 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
                                                             h->l2part.p, h->z_parts, h->lseA, h->lseT, h->inv_zt.p, h->stats.p, rowaux);
     LAUNCH_CHECK("row_norm");
     const long long nq = (long long)h->N * (h->Ke / 4);
-    k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->Sx.p, h->inv_zt.p, h->N, h->Ke, h->Sxs.p);
+    k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, h->N, h->Ke, h->Sxs.p);
     LAUNCH_CHECK("scale_rows");
   } else if (h->x3) {
     // parity mode on tensor cores: exact row pass every iteration, P written as three bf16 planes
@@ -524,7 +572,7 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
     mark(h, s, "tc_gemm_fwd");
   } else {
     GemmArgs g;
-    g.A = h->Pf.p; g.lda = h->ld; g.B = h->Sx.p; g.ldb = h->Ke;
+    g.A = h->Pf.p; g.lda = h->ld; g.B = s_act(h); g.ldb = h->Ke;
     g.M = h->V; g.N = h->Ke; g.K = h->N;
     g.k_per_split = (int)round_up(ceil_div(h->N, h->fwd_splits), 16);
     EpiStorePartial epi{out, h->Ke, vk};
@@ -541,10 +589,18 @@ extern "C" int tgb200_step_begin(tgb200_mapper* h, void* stream) {
   CK(cudaSetDevice(h->cfg.device));
   CKS(check_ready(h));
   if (h->in_step) return fail(TGB200_ERR_STATE, "step_begin called twice without step_end");
+  if (h->constrained) {
+    // f = sigmoid(F), S_f = f o S_ext (:507, :519) and the operand copies the contractions read
+    const long long nq = (long long)h->N * (h->Ke / 4);
+    k_filter_prepare<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->Fl.p, h->Sx.p, h->N, h->Ke, h->fsig.p, h->Sf.p);
+    LAUNCH_CHECK("filter_prepare");
+    CKS(refresh_bf16_operands(h, s));
+  }
   CKS(forward_pass(h, s, h->cfg.lambda_r != 0.f ? 1 : 0));
   const size_t vk = (size_t)h->V * h->Ke;
-  if (needs_rowscalars(h->cfg)) {
-    k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, needs_rowaux(h->cfg) ? h->rowaux.p : nullptr, h->N, h->Y.p + vk);
+  if (needs_rowscalars(h->cfg) || h->constrained) {
+    k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, needs_rowaux(h->cfg) ? h->rowaux.p : nullptr,
+                                           h->constrained ? h->fsig.p : nullptr, h->N, h->Y.p + vk);
     LAUNCH_CHECK("row_scalar_reduce");
   }
   if (h->cfg.n_cells_global != h->N && h->fwd_splits > 1) {
@@ -559,7 +615,7 @@ extern "C" int tgb200_step_begin(tgb200_mapper* h, void* stream) {
 extern "C" int tgb200_exchange_buffer(tgb200_mapper* h, float** device_ptr, int64_t* n_floats) {
   if (!h || !device_ptr || !n_floats) return fail(TGB200_ERR_INVALID, "null argument");
   *device_ptr = h->Y.p;
-  *n_floats = (int64_t)h->V * h->Ke + 4;
+  *n_floats = (int64_t)h->V * h->Ke + kTail;
   return TGB200_OK;
 }
 
@@ -648,14 +704,14 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
   const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
   if (h->tcm) {
-    CKS(tc_rowdot(h->tc, h->Pb.p, nvp, h->dYb.p, vkp, h->n_pairs, h->Sxb.p, h->x3 ? h->Sx.p : nullptr, h->rpart.p, h->N, h->V,
+    CKS(tc_rowdot(h->tc, h->Pb.p, nvp, h->dYb.p, vkp, h->n_pairs, h->Sxb.p, h->x3 ? s_act(h) : nullptr, h->rpart.p, h->N, h->V,
                   h->Ke, h->ld, h->rd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_rowdot");
   } else {
     GemmArgs g;
     g.A = h->Pf.p; g.lda = h->ld; g.B = h->dY.p; g.ldb = h->Ke;
     g.M = h->N; g.N = h->Ke; g.K = h->V; g.k_per_split = (int)round_up(h->V, 16);
-    EpiRowDot epi{h->Sx.p, h->Ke, h->rpart.p};
+    EpiRowDot epi{s_act(h), h->Ke, h->rpart.p};
     dim3 grid((unsigned)ceil_div(h->Ke, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
     k_gemm_simt<true, false, EpiRowDot><<<grid, SG_THREADS, 0, s>>>(g, epi);
     LAUNCH_CHECK("simt_gemm_rowdot");
@@ -667,6 +723,12 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p, h->stats.p, nullptr);
   }
   LAUNCH_CHECK("rowdot_finalize");
+  if (h->constrained) {
+    const AdamScalarsF af{a.one_minus_beta1, a.beta2, a.one_minus_beta2, a.step_size, a.bc2_sqrt, a.eps};
+    k_filter_update<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->N, h->rdot.p, h->fsig.p, h->fscal.p, h->cfg.lambda_count,
+                                                                   h->cfg.lambda_f_reg, af, h->Fl.p, h->mF.p, h->vF.p);
+    LAUNCH_CHECK("filter_update");
+  }
   if (h->bf16) {
     TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, reinterpret_cast<const RowConst*>(h->rowc.p), h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
                   nullptr, nullptr, h->Pb.p, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p};
@@ -682,7 +744,7 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     mark(h, s, "tc_gemm_bwd_adam");
   } else {
     GemmArgs g;
-    g.A = h->Sx.p; g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
+    g.A = s_act(h); g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
     g.M = h->N; g.N = h->V; g.K = h->Ke; g.k_per_split = h->Ke;
     EpiAdam epi{h->M.p, h->m.p, h->v.p, h->ld, h->V, h->stats.p, h->rdot.p, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
     dim3 grid((unsigned)ceil_div(h->V, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
@@ -822,7 +884,7 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   k_col_finalize<<<dim3((unsigned)ceil_div(h->Ke, 128), 3), 128, 0, s>>>(h->colpart.p, h->nchunk, 3, h->Ke, h->colfin.p);
   LAUNCH_CHECK("col_finalize");
   p.colpart = h->colfin.p;
-  k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, nullptr, h->N, h->Y.p + (size_t)h->V * h->Ke);
+  k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, nullptr, nullptr, h->N, h->Y.p + (size_t)h->V * h->Ke);
   LAUNCH_CHECK("row_scalar_reduce");
   k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->ncolchunk, hist.p);
   LAUNCH_CHECK("loss_scalars");

@@ -346,3 +346,124 @@ class Mapper:
         n = ctypes.c_int64()
         _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))
         return n.value
+
+
+class MapperConstrained:
+    """Drop-in for the reference `MapperConstrained` (mapping_optimizer.py:411-639): same constructor keywords,
+    `train()` returns `(mapping, F_out, training_history)` with the reference's history conventions (all values are
+    strings, :630).  The per-cell filter rides the same kernels: S_f = sigmoid(F) o S is the operand of all three
+    contractions, dL/df_i is the row-dot the backward pass needs anyway, and F gets its own small Adam kernel."""
+
+    def __init__(self, S, G, d, lambda_d=1, lambda_g1=1, lambda_g2=1, lambda_r=0, lambda_count=1, lambda_f_reg=1,
+                 target_count=None, device="cuda:0", adata_map=None, random_state=None, *, precision="bf16x3",
+                 M0=None, F0=None):
+        if adata_map is not None:
+            raise NotImplementedError      # the reference raises here too (:476-477)
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {list(_lib.PREC)}")
+        self._lib = _lib.load()
+        self._h = None
+        self.random_state = random_state
+        S = np.ascontiguousarray(np.asarray(S, dtype=np.float32))
+        G = np.ascontiguousarray(np.asarray(G, dtype=np.float32))
+        n_cells, n_voxels, n_genes = S.shape[0], G.shape[0], S.shape[1]
+        self.target_density_enabled = d is not None
+        if M0 is None or F0 is None:
+            # :472-493 -- M is drawn twice (the second draw is used), F after it, legacy numpy RNG
+            if self.random_state:
+                np.random.seed(seed=self.random_state)
+            np.random.normal(0, 1, (n_cells, n_voxels))
+            M0 = np.random.normal(0, 1, (n_cells, n_voxels))
+            F0 = np.random.normal(0, 1, n_cells)
+        cfg = _lib.Config()
+        cfg.struct_size = ctypes.sizeof(_lib.Config)
+        cfg.device = _device_index(device)
+        cfg.n_cells, cfg.n_voxels, cfg.n_genes, cfg.n_types = n_cells, n_voxels, n_genes, 0
+        cfg.n_cells_global = n_cells
+        cfg.precision = _lib.PREC[precision]
+        cfg.density_mode = _lib.DENSITY_CELLS if self.target_density_enabled else _lib.DENSITY_NONE
+        cfg.lambda_g1, cfg.lambda_d, cfg.lambda_g2, cfg.lambda_r = lambda_g1, lambda_d, lambda_g2, lambda_r
+        cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps = 0.9, 0.999, 1e-8
+        cfg.constrained = 1
+        cfg.lambda_count, cfg.lambda_f_reg = lambda_count, lambda_f_reg
+        cfg.target_count = float(n_voxels if target_count is None else target_count)      # :480-483
+        self._lam = dict(g1=lambda_g1, d=lambda_d, g2=lambda_g2, r=lambda_r, c=lambda_count, f=lambda_f_reg)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.tgb200_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h, self._cfg = h, cfg
+        self.n_cells, self.n_voxels, self.n_genes = n_cells, n_voxels, n_genes
+        L = self._lib
+        _lib.check(L.tgb200_set_expression(h, _lib.ptr(S), _lib.ptr(G), None))
+        if self.target_density_enabled:
+            dd = np.ascontiguousarray(np.asarray(d, dtype=np.float32))
+            _lib.check(L.tgb200_set_density(h, _lib.ptr(dd), None, None))
+        _lib.check(L.tgb200_set_mapping(h, _lib.ptr(np.ascontiguousarray(M0, dtype=np.float32)), None))
+        _lib.check(L.tgb200_set_filter(h, _lib.ptr(np.ascontiguousarray(F0, dtype=np.float32)), None))
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.tgb200_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    @staticmethod
+    def _print_line(vals):
+        names = ["Score", "VG reg", "KL reg", "Entropy reg", "Count reg", "Lambda f reg"]          # :555-562
+        msg = ["{}: {:.3f}".format(n, v) for n, v in zip(names, vals) if not np.isnan(v)]
+        return str(msg).replace("[", "").replace("]", "").replace("'", "")
+
+    def train(self, num_epochs, learning_rate=0.1, print_each=100):
+        """mapping_optimizer.py:589-639."""
+        keys = ["total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg", "count_reg", "lambda_f_reg"]
+        first = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
+        first = first.value
+        t = 0
+        while t < num_epochs:
+            chunk = min(num_epochs - t, print_each - (t % print_each)) if print_each else num_epochs - t
+            _lib.check(self._lib.tgb200_run(self._h, chunk, float(learning_rate), None))
+            if print_each and t % print_each == 0:
+                print(self._print_line(self._row_values(first + t)))
+            t += chunk
+        rows = np.empty((num_epochs, _lib.HIST_COLS), dtype=np.float32)
+        if num_epochs:
+            _lib.check(self._lib.tgb200_get_history(self._h, first, num_epochs, _lib.ptr(rows), None))
+        self.history_matrix = rows
+        hist = {k: [] for k in keys}
+        for r in rows:
+            vals = self._values_from_row(r)
+            hist["total_loss"].append("tensor({:.4f}, grad_fn=<AddBackward0>)".format(float(r[0])))     # str(tensor), :630
+            for k, v in zip(keys[1:], vals):
+                hist[k].append(str(v))
+        output = _pinned_empty((self.n_cells, self.n_voxels))
+        _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(output), None))
+        F_out = np.empty(self.n_cells, dtype=np.float32)
+        _lib.check(self._lib.tgb200_get_filter(self._h, None, _lib.ptr(F_out), None))
+        return output, F_out, hist
+
+    def _values_from_row(self, r):
+        """(main_loss, vg_reg, kl_reg, entropy_reg, count_reg, lambda_f_reg) with the reference's sign/NaN conventions."""
+        ent = -float(r[4])            # the reference logs +sum(P log P) here (:526, :540)
+        return (float(r[1]), float(r[2]), float(r[3]), ent, float(r[10]), float(r[11]))
+
+    def _row_values(self, idx):
+        row = np.empty((1, _lib.HIST_COLS), dtype=np.float32)
+        _lib.check(self._lib.tgb200_get_history(self._h, idx, 1, _lib.ptr(row), None))
+        return self._values_from_row(row[0])
+
+    def filter_logits(self):
+        F = np.empty(self.n_cells, dtype=np.float32)
+        _lib.check(self._lib.tgb200_get_filter(self._h, _lib.ptr(F), None, None))
+        return F
+
+    def state(self):
+        M = np.empty((self.n_cells, self.n_voxels), dtype=np.float32)
+        step = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_get_state(self._h, _lib.ptr(M), None, None, ctypes.byref(step), None))
+        return M, self.filter_logits(), step.value
+
+
+MapperConstrained.project = Mapper.project
+MapperConstrained.kernel_launches = Mapper.kernel_launches

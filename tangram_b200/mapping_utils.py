@@ -135,10 +135,6 @@ def map_cells_to_space(
         raise ValueError("A cluster_label must be specified if mode is 'clusters'.")
     if mode == "constrained" and not all([target_count, lambda_f_reg, lambda_count]):
         raise ValueError("target_count, lambda_f_reg and lambda_count must be specified if mode is 'constrained'.")
-    if mode == "constrained":
-        # MapperConstrained (mapping_optimizer.py:411-639) is outside the accelerated path
-        raise NotImplementedError("mode='constrained' is not accelerated by tangram_b200; use the reference")
-
     if mode == "clusters":
         adata_sc = adata_to_cluster_expression(adata_sc, cluster_label, scale, add_density=True)
 
@@ -172,6 +168,7 @@ def map_cells_to_space(
         d = density_prior
     if mode == "clusters":
         d_source = np.array(adata_sc.obs["cluster_density"])
+    if mode in ["clusters", "constrained"]:                                       # :300-307
         if density_prior is None:
             d = adata_sp.obs["uniform_density"]
             d_str = "uniform"
@@ -183,6 +180,8 @@ def map_cells_to_space(
     print_each = 100 if verbose else None
 
     voxel_weights, neighborhood_filter, ct_encode, spatial_weights = None, None, None, None   # :317-329
+    if mode == "constrained":
+        lambda_neighborhood_g1 = lambda_ct_islands = lambda_getis_ord = lambda_moran = lambda_geary = 0   # not used there (:366-375)
     if lambda_neighborhood_g1 > 0:
         voxel_weights = sw.spatial_weights(adata_sp, standardized=True, self_inclusion=True)
     if lambda_ct_islands > 0:
@@ -203,17 +202,29 @@ def map_cells_to_space(
         "ct_encode": ct_encode, "lambda_getis_ord": lambda_getis_ord, "spatial_weights": spatial_weights,
     }
     logging.info("Begin training with {} genes and {} density_prior in {} mode...".format(len(training_genes), d_str, mode))
-    mapper = mo.Mapper(S=S, G=G, d=None if d is None else np.asarray(d, dtype=np.float32), device=device,
-                       random_state=random_state, precision=precision, **hyperparameters)
-    mapping_matrix, training_history = mapper.train(
-        learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
+    F_out = None
+    if mode == "constrained":                                                     # :366-389
+        mapper = mo.MapperConstrained(
+            S=S, G=G, d=None if d is None else np.asarray(d, dtype=np.float32), device=device, random_state=random_state,
+            precision=precision, lambda_d=lambda_d, lambda_g1=lambda_g1, lambda_g2=lambda_g2, lambda_r=lambda_r,
+            lambda_count=lambda_count, lambda_f_reg=lambda_f_reg, target_count=target_count)
+        mapping_matrix, F_out, training_history = mapper.train(
+            learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
+    else:
+        mapper = mo.Mapper(S=S, G=G, d=None if d is None else np.asarray(d, dtype=np.float32), device=device,
+                           random_state=random_state, precision=precision, **hyperparameters)
+        mapping_matrix, training_history = mapper.train(
+            learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
 
     logging.info("Saving results..")
     adata_map = make_adata(X=mapping_matrix, obs=adata_sc[:, training_genes].obs.copy(),
                            var=adata_sp[:, training_genes].obs.copy())
 
+    if mode == "constrained":
+        adata_map.obs["F_out"] = F_out                                            # :398-399
+
     # per-gene training score (:401-410): softmax(M)^T S on the device instead of a host GEMM
-    G_predicted = mapper.project(S)
+    G_predicted = mapper.project(S) if hasattr(mapper, "project") else np.asarray(mapping_matrix).T @ S
     num = (G * G_predicted).sum(axis=0)
     den = np.linalg.norm(G, axis=0) * np.linalg.norm(G_predicted, axis=0)
     df_cs = pd.DataFrame(num / den, list(training_genes), columns=["train_score"])

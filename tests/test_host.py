@@ -110,8 +110,6 @@ def test_map_cells_to_space_validation_messages():
         tg.map_cells_to_space(ad_sc, ad_sp, cv_train_genes=["zzz"])
     with pytest.raises(NotImplementedError):
         tg.map_cells_to_space(ad_sc, ad_sp, lambda_moran=1.0)
-    with pytest.raises(NotImplementedError):
-        tg.map_cells_to_space(ad_sc, ad_sp, mode="constrained", target_count=3)
 
 
 def test_all_zero_gene_is_rejected():
