@@ -829,6 +829,9 @@ constexpr int TC_FWD_BN = 256, TC_FWD_STAGES = 4;
 #ifndef TGB_BWD_STAGES
 #define TGB_BWD_STAGES 3
 #endif
+#ifndef TGB_BWD_POLICY_A
+#define TGB_BWD_POLICY_A kPolicyEvictNormal
+#endif
 #ifndef TGB_BWD_BN
 #define TGB_BWD_BN 256
 #endif
@@ -933,7 +936,7 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_
   TcEpiAdam epi{a, N};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(V, TC_BWD_BN);
   kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, n_pairs, me[0], me[1], me[2], Ke, Ke, tm, tn, 1,
-                                                                              kPolicyEvictNormal, kPolicyEvictLast, epi);
+                                                                              TGB_BWD_POLICY_A, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 

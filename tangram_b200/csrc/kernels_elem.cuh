@@ -266,45 +266,50 @@ struct LossParams {
 // rows_per_block (<= kLossRowsMax) is chosen on the host so that small problems still fill the GPU
 // and large ones (V = 50k) keep the partial arrays small.
 constexpr int kLossRowsMax = 128;
+constexpr int kLossVec = 4;                       // columns per thread (float4)
+constexpr int kLossColsBlk = kLossCols * kLossVec;  // columns per CTA
 __global__ void __launch_bounds__(kLossCols)
 k_loss_reduce(LossParams p, const float* __restrict__ part, int nsplit, int row_stats, int rows_per_block) {
   __shared__ float shr[4][kLossRowsMax][2];
-  const int k = blockIdx.x * kLossCols + threadIdx.x;
+  const int k = blockIdx.x * kLossColsBlk + threadIdx.x * kLossVec;   // Ke is a multiple of 64: whole float4s
   const int j0 = blockIdx.y * rows_per_block;
   const size_t plane = (size_t)p.V * p.Ke;
-  const bool in = k < p.Ke, gene = k < p.K;
+  const bool in = k < p.Ke;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool writeY = nsplit > 1 || part != p.Y;
-  float dot = 0.f, ny2 = 0.f, ys = 0.f;
+  float dot[4] = {0.f, 0.f, 0.f, 0.f}, ny2[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f};
   const int nrows = min(rows_per_block, p.V - j0);
   for (int r = 0; r < nrows; ++r) {
     const int j = j0 + r;
-    float y = 0.f, g = 0.f;
+    float a = 0.f, b = 0.f;
     if (in) {
       const size_t o = (size_t)j * p.Ke + k;
-      if (nsplit == 1) {
-        y = part[o];
-      } else {
-        int z = 0;
-        for (; z + 4 <= nsplit; z += 4) {          // independent loads in flight
-          const float a0 = part[(size_t)z * plane + o], a1 = part[(size_t)(z + 1) * plane + o];
-          const float a2 = part[(size_t)(z + 2) * plane + o], a3 = part[(size_t)(z + 3) * plane + o];
-          y += (a0 + a1) + (a2 + a3);
-        }
-        for (; z < nsplit; ++z) y += part[(size_t)z * plane + o];
+      float4 y = *reinterpret_cast<const float4*>(part + o);
+      for (int z = 1; z < nsplit; ++z) {
+        const float4 t = *reinterpret_cast<const float4*>(part + (size_t)z * plane + o);
+        y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
       }
-      if (writeY) p.Y[o] = y;
-      if (gene) { g = p.G[o]; dot += y * g; ny2 += y * y; ys += y; }
+      if (writeY) *reinterpret_cast<float4*>(p.Y + o) = y;
+      const float4 g = *reinterpret_cast<const float4*>(p.G + o);
+      const float yv[4] = {y.x, y.y, y.z, y.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (k + e < p.K) {
+          dot[e] += yv[e] * gv[e]; ny2[e] += yv[e] * yv[e]; ys[e] += yv[e];
+          a += yv[e] * gv[e]; b += yv[e] * yv[e];
+        }
+      }
     }
     if (row_stats) {
-      float a = gene ? y * g : 0.f, b = gene ? y * y : 0.f;
       a = warp_sum(a); b = warp_sum(b);
       if (lane == 0) { shr[wid][r][0] = a; shr[wid][r][1] = b; }
     }
   }
   if (in) {
     float* cp = p.colpart + (size_t)blockIdx.y * 3 * p.Ke;
-    cp[k] = dot; cp[p.Ke + k] = ny2; cp[2 * p.Ke + k] = ys;
+    *reinterpret_cast<float4*>(cp + k) = make_float4(dot[0], dot[1], dot[2], dot[3]);
+    *reinterpret_cast<float4*>(cp + p.Ke + k) = make_float4(ny2[0], ny2[1], ny2[2], ny2[3]);
+    *reinterpret_cast<float4*>(cp + 2 * p.Ke + k) = make_float4(ys[0], ys[1], ys[2], ys[3]);
   }
   if (row_stats) {
     __syncthreads();
@@ -515,49 +520,54 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
 // tensor-core path, bf16.
 __global__ void __launch_bounds__(kLossCols)
 k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ dYb, Split3 split) {
-  const int k = blockIdx.x * kLossCols + threadIdx.x;
+  const int k0 = (blockIdx.x * kLossCols + threadIdx.x) * kLossVec;     // four columns per thread
   const int j = blockIdx.y;
-  if (k >= p.Ke) return;
-  const size_t o = (size_t)j * p.Ke + k;
-  float dy = 0.f;
-  if (k < p.K) {
-    const float y = p.Y[o], g = p.G[o];
-    dy = -(p.coefA[k] * g - p.coefB[k] * y);
-    if (p.lam_g2 != 0.f) dy -= p.coefAr[j] * g - p.coefBr[j] * y;
-    if (p.lam_nb > 0.f) {
-      const float a = p.coefAn[k], b = p.coefBn[k];
-      float acc = 0.f;
-      for (int e = p.WT.indptr[j]; e < p.WT.indptr[j + 1]; ++e) {
-        const size_t q = (size_t)p.WT.indices[e] * p.Ke + k;
-        acc += p.WT.vals[e] * (a * p.WG[q] - b * p.Z[q]);
+  if (k0 >= p.Ke) return;
+  const size_t o = (size_t)j * p.Ke + k0;
+  const float4 y4 = *reinterpret_cast<const float4*>(p.Y + o);
+  const float4 g4 = *reinterpret_cast<const float4*>(p.G + o);
+  const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+  float out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = k0 + e;
+    float dy = 0.f;
+    if (k < p.K) {
+      const float y = yv[e], g = gv[e];
+      dy = -(p.coefA[k] * g - p.coefB[k] * y);
+      if (p.lam_g2 != 0.f) dy -= p.coefAr[j] * g - p.coefBr[j] * y;
+      if (p.lam_nb > 0.f) {
+        const float a = p.coefAn[k], b = p.coefBn[k];
+        float acc = 0.f;
+        for (int q = p.WT.indptr[j]; q < p.WT.indptr[j + 1]; ++q) {
+          const size_t w = (size_t)p.WT.indices[q] * p.Ke + k;
+          acc += p.WT.vals[q] * (a * p.WG[w] - b * p.Z[w]);
+        }
+        dy -= acc;
       }
-      dy -= acc;
-    }
-    if (p.lam_go > 0.f) {
-      const float a = p.coefAg[k], b = p.coefBg[k];
-      float acc = 0.f;
-      for (int e = p.AT.indptr[j]; e < p.AT.indptr[j + 1]; ++e) {
-        const size_t q = (size_t)p.AT.indices[e] * p.Ke + k;
-        acc += p.AT.vals[e] * (a * p.AG[q] - b * p.Zg[q]);
+      if (p.lam_go > 0.f) {
+        const float a = p.coefAg[k], b = p.coefBg[k];
+        float acc = 0.f;
+        for (int q = p.AT.indptr[j]; q < p.AT.indptr[j + 1]; ++q) {
+          const size_t w = (size_t)p.AT.indices[q] * p.Ke + k;
+          acc += p.AT.vals[q] * (a * p.AG[w] - b * p.Zg[w]);
+        }
+        dy -= acc;
       }
-      dy -= acc;
+    } else if (k < p.K + 2) {
+      dy = (p.density_mode != 0) ? p.densg[j] : 0.f;
+    } else if (k < p.ct_off + p.T && p.lam_ct > 0.f) {
+      const int t = k - p.ct_off;
+      float acc = p.H[(size_t)j * p.T + t];
+      for (int q = p.FT.indptr[j]; q < p.FT.indptr[j + 1]; ++q)
+        acc -= p.FT.vals[q] * p.H[(size_t)p.FT.indices[q] * p.T + t];
+      dy = p.lam_ct * acc / ((float)p.V * (float)p.T);
     }
-  } else if (k < p.K + 2) {
-    dy = (p.density_mode != 0) ? p.densg[j] : 0.f;
-  } else if (k < p.ct_off + p.T && p.lam_ct > 0.f) {
-    const int t = k - p.ct_off;
-    float acc = p.H[(size_t)j * p.T + t];
-    for (int e = p.FT.indptr[j]; e < p.FT.indptr[j + 1]; ++e)
-      acc -= p.FT.vals[e] * p.H[(size_t)p.FT.indices[e] * p.T + t];
-    dy = p.lam_ct * acc / ((float)p.V * (float)p.T);
+    out[e] = dy;
   }
-  if (dY != nullptr) dY[o] = dy;
-  if (dYb != nullptr) dYb[o] = __float2bfloat16_rn(dy);
-  if (split.base != nullptr) {
-    __nv_bfloat16 h, m, l;
-    split3(dy, h, m, l);
-    split.base[o] = h; split.base[split.plane + o] = m; split.base[2 * split.plane + o] = l;
-  }
+  if (dY != nullptr) *reinterpret_cast<float4*>(dY + o) = make_float4(out[0], out[1], out[2], out[3]);
+  if (dYb != nullptr) store_p4<__nv_bfloat16>(dYb + o, out[0], out[1], out[2], out[3]);
+  if (split.base != nullptr) store_split4(split, o, out[0], out[1], out[2], out[3]);
 }
 
 // ------------------------------------------------------------------------------------

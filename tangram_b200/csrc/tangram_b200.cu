@@ -110,7 +110,7 @@ struct tgb200_mapper {
   DevBuf<float> colpart, colpart_nb, colpart_go, rowpart, ctpart;
   DevBuf<float> coefA, coefB, coefAn, coefBn, coefAg, coefBg, coefAr, coefBr, densg;
   CsrDev W, WT, F, FT, A, AT;
-  int nchunk = 0, ncolchunk = 0, n_ct_blocks = 0, loss_rows = 16;
+  int nchunk = 0, ncolchunk = 0, nredchunk = 0, n_ct_blocks = 0, loss_rows = 16;
   DevBuf<float> colfin;         // finalised per-gene sums: [3 | 2 | 2][Ke]
   // history
   DevBuf<float> hist;
@@ -248,6 +248,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   h->nchunk = (int)ceil_div(h->V, h->loss_rows);
   A(h->colfin.alloc((size_t)7 * h->Ke));
   h->ncolchunk = (int)ceil_div(h->Ke, kLossCols);
+  h->nredchunk = (int)ceil_div(h->Ke, kLossColsBlk);
   A(h->colpart.alloc((size_t)h->nchunk * 3 * h->Ke));
   A(h->coefA.alloc(h->Ke)); A(h->coefB.alloc(h->Ke));
   A(h->densg.alloc(h->V));
@@ -639,10 +640,11 @@ static int ensure_history(tgb200_mapper* h, int64_t need, cudaStream_t s) {
 static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool reduce_partials_first) {
   LossParams p = make_loss_params(h);
   const tgb200_config& c = h->cfg;
-  dim3 rgrid(h->ncolchunk, h->nchunk);
+  dim3 rgrid(h->ncolchunk, h->nchunk);          // spatial kernels: one column per thread
+  dim3 vgrid(h->nredchunk, h->nchunk);          // reduction kernel: four columns per thread
   const float* part = (h->fwd_splits > 1 && reduce_partials_first) ? h->Ypart.p : h->Y.p;
   const int nsplit = (h->fwd_splits > 1 && reduce_partials_first) ? h->fwd_splits : 1;
-  k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, nsplit, c.lambda_g2 != 0.f ? 1 : 0, h->loss_rows);
+  k_loss_reduce<<<vgrid, kLossCols, 0, s>>>(p, part, nsplit, c.lambda_g2 != 0.f ? 1 : 0, h->loss_rows);
   LAUNCH_CHECK("loss_reduce");
   const dim3 fgrid3((unsigned)ceil_div(h->Ke, 128), 3), fgrid2((unsigned)ceil_div(h->Ke, 128), 2);
   k_col_finalize<<<fgrid3, 128, 0, s>>>(h->colpart.p, h->nchunk, 3, h->Ke, h->colfin.p);
@@ -666,9 +668,9 @@ static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool re
     k_ct_islands<<<h->n_ct_blocks, 256, 0, s>>>(p);
     LAUNCH_CHECK("ct_islands");
   }
-  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->ncolchunk, hist_row);
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->nredchunk, hist_row);
   LAUNCH_CHECK("loss_scalars");
-  dim3 dgrid(h->ncolchunk, h->V);
+  dim3 dgrid(h->nredchunk, h->V);
   // the tensor-core path consumes only the bf16 copy of dY_ext
   k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->tcm ? nullptr : h->dY.p, h->bf16 ? h->dYb.p : nullptr,
                                             h->x3 ? Split3{h->dYb.p, (size_t)h->V * h->Ke} : Split3{nullptr, 0});
@@ -877,7 +879,7 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   CKS(hist.alloc(TGB200_HIST_COLS));
   p.rowpart = rowpart.p; p.coefAr = coefAr.p; p.coefBr = coefBr.p;
   p.lam_g2 = 1.f; p.lam_g1 = 1.f; p.lam_nb = 0.f; p.lam_go = 0.f; p.lam_ct = 0.f; p.density_mode = 0;
-  dim3 rgrid(h->ncolchunk, h->nchunk);
+  dim3 rgrid(h->nredchunk, h->nchunk);
   const float* part = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
   k_loss_reduce<<<rgrid, kLossCols, 0, s>>>(p, part, h->fwd_splits, 1, h->loss_rows);
   LAUNCH_CHECK("loss_reduce");
@@ -886,7 +888,7 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   p.colpart = h->colfin.p;
   k_row_scalar_reduce<<<1, 1024, 0, s>>>(h->stats.p, nullptr, nullptr, h->N, h->Y.p + (size_t)h->V * h->Ke);
   LAUNCH_CHECK("row_scalar_reduce");
-  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->ncolchunk, hist.p);
+  k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->nredchunk, hist.p);
   LAUNCH_CHECK("loss_scalars");
   // sparsity-weighted gene score needs per-gene cosines: recover them from coefA/coefB on the host
   std::vector<float> hrow(TGB200_HIST_COLS), cA(h->K), cB(h->K), Gh((size_t)h->V * h->Ke), tail(4);
