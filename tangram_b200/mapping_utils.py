@@ -89,52 +89,41 @@ def adata_to_cluster_expression(adata, cluster_label, scale=True, add_density=Tr
     return ret
 
 
+def _validate_mapping_args(mode, cluster_label, lambda_g1, lambda_d, density_prior, target_count, lambda_f_reg, lambda_count):
+    """Argument checks of the reference entry point, same order and messages (mapping_utils.py:206-229).
+    Returns the effective lambda_d (a density prior switches the density term on, :214-215)."""
+    if lambda_g1 == 0:
+        raise ValueError("lambda_g1 cannot be 0.")
+    if isinstance(density_prior, str) and density_prior not in ("rna_count_based", "uniform"):
+        raise ValueError("Invalid input for density_prior.")
+    if density_prior is not None and not lambda_d:
+        lambda_d = 1
+    checks = (
+        (lambda_d > 0 and density_prior is None, "When lambda_d is set, please define the density_prior."),
+        (mode not in ("clusters", "cells", "constrained"), 'Argument "mode" must be "cells", "clusters" or "constrained'),
+        (mode == "clusters" and cluster_label is None, "A cluster_label must be specified if mode is 'clusters'."),
+        (mode == "constrained" and not all([target_count, lambda_f_reg, lambda_count]),
+         "target_count, lambda_f_reg and lambda_count must be specified if mode is 'constrained'."),
+    )
+    for failed, message in checks:
+        if failed:
+            raise ValueError(message)
+    return lambda_d
+
+
 def map_cells_to_space(
-    adata_sc,
-    adata_sp,
-    cv_train_genes=None,
-    cluster_label=None,
-    mode="cells",
-    device="cuda:0",
-    learning_rate=0.1,
-    num_epochs=1000,
-    scale=True,
-    lambda_d=0,
-    lambda_g1=1,
-    lambda_g2=0,
-    lambda_r=0,
-    lambda_l1=0,
-    lambda_l2=0,
-    lambda_count=1,
-    lambda_f_reg=1,
-    target_count=None,
-    lambda_neighborhood_g1=0,
-    lambda_ct_islands=0,
-    lambda_getis_ord=0,
-    lambda_moran=0,
-    lambda_geary=0,
-    random_state=None,
-    verbose=True,
-    density_prior="rna_count_based",
-    precision="bf16x3",
+    adata_sc, adata_sp, cv_train_genes=None, cluster_label=None, mode="cells", device="cuda:0",
+    learning_rate=0.1, num_epochs=1000, scale=True,
+    lambda_d=0, lambda_g1=1, lambda_g2=0, lambda_r=0, lambda_l1=0, lambda_l2=0,
+    lambda_count=1, lambda_f_reg=1, target_count=None,
+    lambda_neighborhood_g1=0, lambda_ct_islands=0, lambda_getis_ord=0, lambda_moran=0, lambda_geary=0,
+    random_state=None, verbose=True, density_prior="rna_count_based", precision="bf16x3",
 ):
     """Same contract as the reference (mapping_utils.py:141-428); `device` must be CUDA.
     `precision` ("bf16x3" parity-grade on tensor cores, default | "fp32" FFMA | "bf16" throughput) is the only added keyword."""
-    # --- argument validation, same order and messages as :206-229
-    if lambda_g1 == 0:
-        raise ValueError("lambda_g1 cannot be 0.")
-    if (type(density_prior) is str) and (density_prior not in ["rna_count_based", "uniform", None]):
-        raise ValueError("Invalid input for density_prior.")
-    if density_prior is not None and (lambda_d == 0 or lambda_d is None):
-        lambda_d = 1
-    if lambda_d > 0 and density_prior is None:
-        raise ValueError("When lambda_d is set, please define the density_prior.")
-    if mode not in ["clusters", "cells", "constrained"]:
-        raise ValueError('Argument "mode" must be "cells", "clusters" or "constrained')
-    if mode == "clusters" and cluster_label is None:
-        raise ValueError("A cluster_label must be specified if mode is 'clusters'.")
-    if mode == "constrained" and not all([target_count, lambda_f_reg, lambda_count]):
-        raise ValueError("target_count, lambda_f_reg and lambda_count must be specified if mode is 'constrained'.")
+    lambda_d = _validate_mapping_args(mode, cluster_label, lambda_g1, lambda_d, density_prior, target_count,
+                                      lambda_f_reg, lambda_count)
+
     if mode == "clusters":
         adata_sc = adata_to_cluster_expression(adata_sc, cluster_label, scale, add_density=True)
 
