@@ -134,6 +134,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
+
 // ---- descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
 // LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
@@ -217,8 +229,8 @@ struct TileCoord {
 struct EpiCtx {
   const CUtensorMap* map[3];   // state arrays (M, m, v) as fp32 2D tensors, box 32 x 32, 128B swizzle
   uint32_t staging;            // shared-memory staging area (1024-byte aligned)
-  uint32_t bars;               // 8 mbarriers: [group 0..3][buffer 0..1]
-  uint32_t use0, use1;         // completed uses of this thread's two staging buffers (mbarrier parity)
+  uint32_t bars;               // 16 mbarriers: [group 0..3][buffer 0..3]
+  uint32_t uses;               // bit b = phase parity of this thread's staging buffer b
 };
 
 struct TcEpiStore {
@@ -328,6 +340,9 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+#ifndef TGB_EPI_SW
+#define TGB_EPI_SW 32
+#endif
 #ifndef TGB_EPI_NBUF
 #define TGB_EPI_NBUF 1
 #endif
@@ -336,15 +351,19 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f
 #endif
 struct TcEpiAdam {
   TcAdamArgs p; int M;
-  static constexpr int CW = 16;                            // columns per warp per staged sub-tile
-  static constexpr int SW = 32;                            // staged sub-tile width (two warps)
-  static constexpr int kArrayBytes = 32 * SW * 4;          // 32 rows x 128 B = 4 KB
+  static constexpr int SW = TGB_EPI_SW;                    // staged sub-tile width (two warps): 32 or 16 columns
+  static constexpr int CW = SW / 2;                        // columns per warp per staged sub-tile
+  static constexpr int VPW = CW / 4;                       // float4 per warp-row per array
+  static constexpr int kArrayBytes = 32 * SW * 4;          // 32 rows x (128 | 64) B
   static constexpr int kBufBytes = 3 * kArrayBytes;        // M, m, v
   static constexpr int NBUF = TGB_EPI_NBUF;                // staging depth per lane quarter
   static constexpr int kGroupBytes = NBUF * kBufBytes;
   static constexpr int kStagingBytes = 4 * kGroupBytes;    // 4 lane quarters
-  // TMA SWIZZLE_128B: 16-byte chunk jj of row r lives at chunk position jj ^ (r & 7)
-  static __device__ __forceinline__ uint32_t swz(int r, int jj) { return (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4)); }
+  // TMA SWIZZLE_128B (128-byte rows): 16-byte chunk jj of row r lives at chunk position jj ^ (r & 7);
+  // TMA SWIZZLE_64B (64-byte rows): at jj ^ ((r >> 1) & 3).  Either way one thread per row is conflict free.
+  static __device__ __forceinline__ uint32_t swz(int r, int jj) {
+    return SW == 32 ? (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4)) : (uint32_t)(r * 64 + ((jj ^ ((r >> 1) & 3)) << 4));
+  }
 
   // bf16-mode arithmetic: approximate MUFU ops (ex2, sqrt, rcp), ~2 ulp -- far below bf16 operand noise
   __device__ __forceinline__ float one(float x, float dp, float& m, float& v, const RowConst& rc, float lse_l2e) const {
@@ -374,7 +393,7 @@ struct TcEpiAdam {
 // so the wider tile (25% fewer operand bytes) and a deeper ring beat a deeper staging pipeline.
   // leader lane of a group: three bulk tensor loads of sub-tile `c` into staging buffer `b`
   __device__ __forceinline__ void issue_loads(const EpiCtx& cx, int g, int b, int row0, int col) const {
-    const uint32_t bar = cx.bars + (uint32_t)(g * 2 + b) * 8u;
+    const uint32_t bar = cx.bars + (uint32_t)(g * 4 + b) * 8u;
     const uint32_t dst = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
     mbar_expect_tx_u32(bar, kBufBytes);
     tma_load_2d_u32(cx.map[0], bar, dst, col, row0, kPolicyEvictFirst);
@@ -403,8 +422,8 @@ struct TcEpiAdam {
   __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx& cx) const {
     static_assert(NW == 8, "two warps per TMEM lane quarter");
     if (ew < 4 && lane == 0) {
-      issue_loads(cx, q, 0, t.m0 + q * 32, t.n0);
-      if (NBUF > 1) issue_loads(cx, q, 1, t.m0 + q * 32, t.n0 + SW);
+#pragma unroll
+      for (int b = 0; b < NBUF; ++b) issue_loads(cx, q, b, t.m0 + q * 32, t.n0 + b * SW);
       for (int k = 0; k < TGB_EPI_L2_AHEAD; ++k) prefetch_l2(cx, t.m0 + q * 32, t.n0 + (NBUF + k) * SW);
     }
   }
@@ -434,16 +453,16 @@ struct TcEpiAdam {
     p0 = fast_ex2(e0); p1 = fast_ex2(e1);
     upk2(x, x0, x1); upk2(m, m0, m1); upk2(v, v0, v1);
   }
-  __device__ __forceinline__ void update_chunk_fast(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[16],
+  __device__ __forceinline__ void update_chunk_fast(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[CW],
                                                     const RowConst& rc, float lse_l2e, float& zs) const {
     PairConsts k;
     k.l2e = pk2(1.4426950408889634f, 1.4426950408889634f); k.nlse = pk2(-lse_l2e, -lse_l2e); k.nr = pk2(-rc.r, -rc.r);
     k.omb1 = pk2(p.a.one_minus_beta1, p.a.one_minus_beta1); k.omb2 = pk2(p.a.one_minus_beta2, p.a.one_minus_beta2);
     k.b2 = pk2(p.a.beta2, p.a.beta2); k.ibc = pk2(p.a.inv_bc2_sqrt, p.a.inv_bc2_sqrt); k.eps = pk2(p.a.eps, p.a.eps);
     k.nstep = pk2(-p.a.step_size, -p.a.step_size);
-    uint32_t pkd[8];
+    uint32_t pkd[2 * VPW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < VPW; ++j) {
       const uint32_t sp = buf + swz(lane, jbase + j);
       float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
       float p0, p1, p2, p3;
@@ -458,8 +477,8 @@ struct TcEpiAdam {
       pkd[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
     }
     uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
-    dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
-    dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
+#pragma unroll
+    for (int u = 0; u < VPW / 2; ++u) dst[u] = make_uint4(pkd[4 * u], pkd[4 * u + 1], pkd[4 * u + 2], pkd[4 * u + 3]);
   }
   // parity-mode update of one 16-column sub-tile: same arithmetic as the FFMA path's EpiAdam (gemm_simt.cuh)
   __device__ __forceinline__ float one_exact(float x, float dp, float& m, float& v, const RowStat& st, float r) const {
@@ -471,10 +490,10 @@ struct TcEpiAdam {
     if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x;
     return adam_update(x, g, m, v, p.a);
   }
-  __device__ __forceinline__ void update_chunk_exact(uint32_t buf, int jbase, int lane, int col0, const float (&acc)[16],
+  __device__ __forceinline__ void update_chunk_exact(uint32_t buf, int jbase, int lane, int col0, const float (&acc)[CW],
                                                      const RowStat& st, float r) const {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < VPW; ++j) {
       const uint32_t sp = buf + swz(lane, jbase + j);
       float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
       const int col = col0 + 4 * j;
@@ -489,12 +508,12 @@ struct TcEpiAdam {
   }
   // one 16-column sub-tile, thread = row.  GUARD=false: all 16 columns are real voxels.
   template <bool GUARD>
-  __device__ __forceinline__ void update_chunk(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[16],
+  __device__ __forceinline__ void update_chunk(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[CW],
                                                const RowConst& rc, float lse_l2e, float& zs, float& pxs, float& l1s,
                                                float& l2s) const {
-    uint32_t pk[8];
+    uint32_t pk[2 * VPW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < VPW; ++j) {
       const uint32_t sp = buf + swz(lane, jbase + j);
       float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
       const int col = col0 + 4 * j;
@@ -512,8 +531,8 @@ struct TcEpiAdam {
     }
     // 16 bf16 = one 32-byte sector per row, written straight from the row-owning thread
     uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
-    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+    for (int u = 0; u < VPW / 2; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
   }
   // ew = epilogue warp index; group = TMEM lane quarter q; part = ew / 4 picks the 16-column half of every
   // 32-column staged sub-tile.
@@ -521,7 +540,7 @@ struct TcEpiAdam {
   __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx& cx) const {
     static_assert(NW == 8, "two warps per TMEM lane quarter");
     constexpr int NCHUNK = BN / SW;
-    static_assert(NCHUNK >= 2, "prologue prefetches two sub-tiles");
+    static_assert(NCHUNK >= NBUF && NBUF <= 4, "prologue prefetches NBUF sub-tiles");
     const int part = ew >> 2;
     const bool leader = (part == 0) && (lane == 0);
     const int row0 = t.m0 + q * 32;
@@ -543,23 +562,23 @@ struct TcEpiAdam {
     TGB_T0();
 #pragma unroll 1
     for (int c = 0; c < NCHUNK; ++c) {
-      const int b = (NBUF > 1) ? (c & 1) : 0;
+      const int b = c % NBUF;
       const uint32_t buf = cx.staging + (uint32_t)(q * kGroupBytes + b * kBufBytes);
       const int colg = t.n0 + c * SW;             // first column of the staged sub-tile
       const int col0 = colg + part * CW;          // first column this warp updates
-      mbar_wait_u32(cx.bars + (uint32_t)(q * 2 + b) * 8u, (b ? cx.use1 : cx.use0) & 1u);
-      if (b) cx.use1++; else cx.use0++;
+      mbar_wait_u32(cx.bars + (uint32_t)(q * 4 + b) * 8u, (cx.uses >> b) & 1u);
+      cx.uses ^= (1u << b);                       // per-buffer phase parity
       TGB_TICK(tw);
-      float acc[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
+      float acc[CW];
+      tmem_ld_cols(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
       if (exact) {
-        if (row < M && col0 < p.V) update_chunk_exact(buf, part * 4, lane, col0, acc, st, rex);
+        if (row < M && col0 < p.V) update_chunk_exact(buf, part * VPW, lane, col0, acc, st, rex);
       } else if (row < M && col0 < p.ld) {
         if (col0 + CW <= p.V) {
-          if (plain) update_chunk_fast(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs);
-          else update_chunk<false>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+          if (plain) update_chunk_fast(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs);
+          else update_chunk<false>(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
         } else {
-          update_chunk<true>(buf, part * 4, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
+          update_chunk<true>(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
         }
       }
       TGB_TICK(tc);
@@ -628,7 +647,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
-  __shared__ __align__(8) uint64_t epi_bar[8];      // epilogue staging: [lane quarter][buffer]
+  __shared__ __align__(8) uint64_t epi_bar[16];     // epilogue staging: [lane quarter][buffer]
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -642,7 +661,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
 #pragma unroll
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
 #pragma unroll
-    for (int b = 0; b < 8; ++b) mbar_init(&epi_bar[b], 1);
+    for (int b = 0; b < 16; ++b) mbar_init(&epi_bar[b], 1);
     if (Epi::kStagingBytes > 0) { tma_prefetch_desc(&map_e0); tma_prefetch_desc(&map_e1); tma_prefetch_desc(&map_e2); }
     fence_barrier_init();
   }
@@ -718,7 +737,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
     cx.map[0] = &map_e0; cx.map[1] = &map_e1; cx.map[2] = &map_e2;
     cx.staging = smem_u32(smem + STAGES * kStageBytes);
     cx.bars = smem_u32(&epi_bar[0]);
-    cx.use0 = 0; cx.use1 = 0;
+    cx.uses = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       TileCoord t;
@@ -803,7 +822,8 @@ static inline int tc_make_map_f32(TcContext& tc, CUtensorMap* map, const void* b
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = tc.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner * 4 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, n, "cuTensorMapEncodeTiled(f32) failed (%d) cols=%llu rows=%llu ld=%llu", (int)r,
@@ -929,7 +949,7 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_
   CUtensorMap me[3];
   float* st[3] = {a.Mp, a.mp, a.vp};
   for (int i = 0; i < 3; ++i)
-    if (tc_make_map_f32(tc, &me[i], st[i], V, N, a.ld, 32, 32, err, n)) return -2;
+    if (tc_make_map_f32(tc, &me[i], st[i], V, N, a.ld, TcEpiAdam::SW, 32, err, n)) return -2;
   auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
   const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
