@@ -115,3 +115,26 @@ def test_tc_resume_reinitialises_row_normalisation():
     assert rel_fro(b, a) < 5e-3
     assert abs(float(hb["total_loss"][-1]) - float(ha["total_loss"][-1])) < 1e-4
     assert abs(hb["entropy_reg"][-1] - ha["entropy_reg"][-1]) < 1e-3 * abs(ha["entropy_reg"][-1])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 1), (5, 130, 2), (130, 65, 3), (129, 257, 65)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_degenerate_and_off_tile_shapes(shape, precision):
+    """One cell, one voxel, one gene, and sizes just past every tile boundary (128 rows, 64/256 columns, 64 genes)."""
+    from tangram_b200 import Mapper
+    N, V, K = shape
+    rng = np.random.default_rng(N * 1000 + V)
+    S = (rng.random((N, K)) + 0.1).astype(np.float32)
+    G = (rng.random((V, K)) + 0.1).astype(np.float32)
+    d = (np.ones(V) / V).astype(np.float32)
+    M0 = rng.standard_normal((N, V)).astype(np.float32)
+    o = OracleMapper(S, G, d=d, lambda_d=1.0, lambda_g2=0.5, M0=M0)
+    oo, oh = o.train(3, print_each=None)
+    m = Mapper(S, G, d=d, lambda_d=1.0, lambda_g2=0.5, M0=M0, device="cuda:0", precision=precision)
+    out, hist = m.train(3, print_each=None)
+    tol = 5e-2 if precision == "bf16" else 2e-5
+    assert out.shape == (N, V) and np.all(np.isfinite(out))
+    assert np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
+    assert rel_fro(out, oo) < tol
+    ltol = 5e-3 if precision == "bf16" else 1e-5
+    assert np.max(np.abs(np.array([float(x) for x in hist["total_loss"]]) - np.array([float(x) for x in oh["total_loss"]]))) < ltol
