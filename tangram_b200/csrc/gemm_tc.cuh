@@ -64,6 +64,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kPolicyEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
+#ifndef TGB_EPI_LD_POLICY
+#define TGB_EPI_LD_POLICY kPolicyEvictFirst   // optimizer state is touched once per step
+#endif
+#ifndef TGB_EPI_ST_POLICY
+#define TGB_EPI_ST_POLICY kPolicyEvictFirst
+#endif
+// one full 32-byte sector per instruction (sm_100+: STG.256) -- 16-byte stores from a row-per-thread layout are partial-sector
+// writes, which cost L2 fill reads from DRAM
+__device__ __forceinline__ void stg256(void* dst, const uint32_t* w) {
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+template <int WORDS>
+__device__ __forceinline__ void store_row_words(void* dst, const uint32_t (&w)[WORDS]) {
+  static_assert(WORDS % 4 == 0, "16-byte multiples");
+#pragma unroll
+  for (int u = 0; u < WORDS / 8; ++u) stg256(reinterpret_cast<uint8_t*>(dst) + 32 * u, &w[8 * u]);
+  if (WORDS % 8) reinterpret_cast<uint4*>(dst)[WORDS / 4 - 1] = make_uint4(w[WORDS - 4], w[WORDS - 3], w[WORDS - 2], w[WORDS - 1]);
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
@@ -79,7 +98,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+#ifdef TGB_PREFETCH_EVICT_LAST
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;"
+               ::"l"(map), "r"(c0), "r"(c1), "l"(kPolicyEvictLast) : "memory");
+#else
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -218,6 +242,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // Coordinates of the work item an epilogue warp is draining.
+// Work item w -> (row tile m, column tile n).  Row tiles are taken in groups of `group_m`; inside a group the order is
+// column-major (all rows of the group for column 0, then column 1, ...).  The CTAs running at the same time then cover
+// the whole group for a few columns: the group's A rows (group_m x 128 x K, re-read for every column) are a small,
+// hot L2 footprint and each B column tile is used in one burst.  group_m = 1 is plain column-fastest order.
+__device__ __forceinline__ void tile_mn(int w, int tiles_m, int tiles_n, int group_m, int& m, int& n) {
+  const int per_group = group_m * tiles_n;
+  const int g = w / per_group, r = w - g * per_group;
+  const int rows = min(group_m, tiles_m - g * group_m);
+  n = r / rows;
+  m = g * group_m + (r - n * rows);
+}
 struct TileCoord {
   int m0, n0;        // first output row / column of the tile
   int tile_n;        // column-tile index
@@ -396,9 +431,9 @@ struct TcEpiAdam {
     const uint32_t bar = cx.bars + (uint32_t)(g * 4 + b) * 8u;
     const uint32_t dst = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
     mbar_expect_tx_u32(bar, kBufBytes);
-    tma_load_2d_u32(cx.map[0], bar, dst, col, row0, kPolicyEvictFirst);
-    tma_load_2d_u32(cx.map[1], bar, dst + kArrayBytes, col, row0, kPolicyEvictFirst);
-    tma_load_2d_u32(cx.map[2], bar, dst + 2 * kArrayBytes, col, row0, kPolicyEvictFirst);
+    tma_load_2d_u32(cx.map[0], bar, dst, col, row0, TGB_EPI_LD_POLICY);
+    tma_load_2d_u32(cx.map[1], bar, dst + kArrayBytes, col, row0, TGB_EPI_LD_POLICY);
+    tma_load_2d_u32(cx.map[2], bar, dst + 2 * kArrayBytes, col, row0, TGB_EPI_LD_POLICY);
   }
   // DRAM -> L2 prefetch of a sub-tile a short, fixed distance ahead of its bulk load (a few microseconds:
   // long enough to hide DRAM latency, short enough that the lines are still in L2 when the load arrives)
@@ -411,9 +446,9 @@ struct TcEpiAdam {
   }
   __device__ __forceinline__ void issue_stores(const EpiCtx& cx, int g, int b, int row0, int col) const {
     const uint32_t src = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
-    tma_store_2d(cx.map[0], src, col, row0, kPolicyEvictFirst);
-    tma_store_2d(cx.map[1], src + kArrayBytes, col, row0, kPolicyEvictFirst);
-    tma_store_2d(cx.map[2], src + 2 * kArrayBytes, col, row0, kPolicyEvictFirst);
+    tma_store_2d(cx.map[0], src, col, row0, TGB_EPI_ST_POLICY);
+    tma_store_2d(cx.map[1], src + kArrayBytes, col, row0, TGB_EPI_ST_POLICY);
+    tma_store_2d(cx.map[2], src + 2 * kArrayBytes, col, row0, TGB_EPI_ST_POLICY);
     bulk_commit();
   }
   // Issued before the wait on the accumulator: the first two sub-tiles are already in flight when the
@@ -476,9 +511,11 @@ struct TcEpiAdam {
       pkd[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
       pkd[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
     }
-    uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
-#pragma unroll
-    for (int u = 0; u < VPW / 2; ++u) dst[u] = make_uint4(pkd[4 * u], pkd[4 * u + 1], pkd[4 * u + 2], pkd[4 * u + 3]);
+#ifndef TGB_SKIP_PWRITE
+    store_row_words(p.Pt + (size_t)row * p.ld + col0, pkd);
+#else
+    if (zs == -1.2345f) *reinterpret_cast<uint4*>(p.Pt) = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
+#endif
   }
   // parity-mode update of one 16-column sub-tile: same arithmetic as the FFMA path's EpiAdam (gemm_simt.cuh)
   __device__ __forceinline__ float one_exact(float x, float dp, float& m, float& v, const RowStat& st, float r) const {
@@ -530,9 +567,7 @@ struct TcEpiAdam {
       pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
     }
     // 16 bf16 = one 32-byte sector per row, written straight from the row-owning thread
-    uint4* dst = reinterpret_cast<uint4*>(p.Pt + (size_t)row * p.ld + col0);
-#pragma unroll
-    for (int u = 0; u < VPW / 2; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    store_row_words(p.Pt + (size_t)row * p.ld + col0, pk);
   }
   // ew = epilogue warp index; group = TMEM lane quarter q; part = ew / 4 picks the 16-column half of every
   // 32-column staged sub-tile.
@@ -632,8 +667,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
           const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
           const __grid_constant__ CUtensorMap map_e2,
-          int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, uint64_t policy_a, uint64_t policy_b,
-          const Epi epi) {
+          int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, int group_m, uint64_t policy_a,
+          uint64_t policy_b, const Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
   using TileB = OperandTile<B_KMAJOR, BN>;
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
@@ -676,9 +711,10 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
     if (lane == 0) {
       uint32_t kbg = 0;                         // k-blocks issued so far (ring position)
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int n0 = (w % tiles_n) * BN;
-        const int m0 = ((w / tiles_n) % tiles_m) * TC_BM;
         const int z = w / (tiles_n * tiles_m);
+        int tm_i, tn_i;
+        tile_mn(w - z * tiles_n * tiles_m, tiles_m, tiles_n, group_m, tm_i, tn_i);
+        const int n0 = tn_i * BN, m0 = tm_i * TC_BM;
         const int k_begin = z * k_per_split;
         const int k_end = min(k_total, k_begin + k_per_split);
         const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
@@ -741,11 +777,12 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       TileCoord t;
-      t.tile_n = w % tiles_n;
+      t.split = w / (tiles_n * tiles_m);
+      int tm_i;
+      tile_mn(w - t.split * tiles_n * tiles_m, tiles_m, tiles_n, group_m, tm_i, t.tile_n);
       t.tiles_n = tiles_n;
       t.n0 = t.tile_n * BN;
-      t.m0 = ((w / tiles_n) % tiles_m) * TC_BM;
-      t.split = w / (tiles_n * tiles_m);
+      t.m0 = tm_i * TC_BM;
       const int b = it & 1;
 #ifndef TGB_SKIP_EPI
       epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
@@ -770,6 +807,202 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- CTA-pair variant (tcgen05 cta_group::2) ----------------------------------------------------
+// Two CTAs of a cluster (ranks 0/1, adjacent SMs) compute one 256 x BN tile: each stages ITS 128 rows of A and
+// HALF of the B tile, rank 0's MMA thread issues M=256 instructions that read both CTAs' shared memory and write
+// rows 0-127 / 128-255 of the tile into the two CTAs' TMEM.  B crosses L2->SM once per 256 output rows instead
+// of once per 128, and a stage is 16 KB smaller per CTA -- room for a deeper epilogue staging pipeline.
+// Protocol (cf. the cluster/2-SM notes in blackwell_cuda_programming.md):
+//   full[s]   lives in rank 0: armed there with both CTAs' bytes; both producers' bulk loads complete_tx on it
+//   empty[s]  one multicast tcgen05.commit per use arrives on BOTH CTAs' barriers (each producer waits locally)
+//   tfull[b]  multicast commit -> each CTA's epilogue waits on its own copy
+//   tempty[b] lives in rank 0: the epilogue warps of both CTAs arrive on it remotely
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major A and B only (the backward contraction).  tiles_m counts 256-row pair tiles; grid = 2 x clusters.
+template <int BN, int STAGES, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
+               const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
+               const __grid_constant__ CUtensorMap map_e2, int k_total, int tiles_m, int tiles_n, int group_m,
+               uint64_t policy_a, uint64_t policy_b, const Epi epi) {
+  using TileA = OperandTile<true, TC_BM>;         // this CTA's 128 rows
+  using TileB = OperandTile<true, BN / 2>;        // this CTA's half of the B tile
+  constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
+  constexpr uint32_t kTmemCols = 2 * BN;
+  static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
+  constexpr uint32_t kIdesc = make_idesc(2 * TC_BM, BN, false, false);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t epi_bar[16];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int total = tiles_m * tiles_n;
+  const int num_kb = (k_total + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps_a.m[0]);
+    tma_prefetch_desc(&maps_b.m[0]);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) mbar_init(&epi_bar[b], 1);
+    if (Epi::kStagingBytes > 0) { tma_prefetch_desc(&map_e0); tma_prefetch_desc(&map_e1); tma_prefetch_desc(&map_e2); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();                           // barriers of both CTAs initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of B, completing on rank 0's full barrier =====
+#ifdef TGB_SKIP_MAINLOOP
+    if (false) {
+#else
+    if (lane == 0) {
+#endif
+      uint32_t kbg = 0;
+      for (int w = cid; w < total; w += ncl) {
+        int tm_i, tn_i;
+        tile_mn(w, tiles_m, tiles_n, group_m, tm_i, tn_i);
+        const int n0 = tn_i * BN + (int)rank * (BN / 2);
+        const int m0 = tm_i * (2 * TC_BM) + (int)rank * TC_BM;
+        for (int pr = 6 - n_pairs; pr < 6; ++pr) {
+          const CUtensorMap* ma = &maps_a.m[kPairA[pr]];
+          const CUtensorMap* mb = &maps_b.m[kPairB[pr]];
+          for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+            const int s = kbg % STAGES;
+            const uint32_t ph = (kbg / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const uint32_t sa = smem_u32(smem + s * kStageBytes);
+            const uint32_t sb = sa + TileA::kBytes;
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            tma_load_2d_pair(ma, lbar, sa, kb * TC_BK, m0, policy_a);
+            tma_load_2d_pair(mb, lbar, sb, kb * TC_BK, n0, policy_b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of rank 0 drives both SMs' tensor cores =====
+    if (lane == 0 && rank == 0) {
+      uint32_t kbg = 0;
+      int it = 0;
+      for (int w = cid; w < total; w += ncl, ++it) {
+        const int b = it & 1;
+        mbar_wait(&tempty_bar[b], (((uint32_t)it >> 1) & 1) ^ 1);   // both epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+#ifdef TGB_SKIP_MAINLOOP
+        const int total_kb = 0;
+#else
+        const int total_kb = num_kb * n_pairs;
+#endif
+        for (int kb = 0; kb < total_kb; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint32_t sb = sa + TileA::kBytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+            umma_bf16_pair(d_tmem, TileA::desc(sa, k), TileB::desc(sb, k), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);
+        }
+        umma_commit_pair(&tfull_bar[b]);
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): each CTA owns 128 rows of the pair tile =====
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    EpiCtx cx;
+    cx.map[0] = &map_e0; cx.map[1] = &map_e1; cx.map[2] = &map_e2;
+    cx.staging = smem_u32(smem + STAGES * kStageBytes);
+    cx.bars = smem_u32(&epi_bar[0]);
+    cx.uses = 0;
+    const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    int it = 0;
+    for (int w = cid; w < total; w += ncl, ++it) {
+      TileCoord t;
+      int tm_i;
+      tile_mn(w, tiles_m, tiles_n, group_m, tm_i, t.tile_n);
+      t.tiles_n = tiles_n;
+      t.n0 = t.tile_n * BN;
+      t.m0 = tm_i * (2 * TC_BM) + (int)rank * TC_BM;
+      t.split = 0;
+      const int b = it & 1;
+#ifndef TGB_SKIP_EPI
+      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
+#endif
+      mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+#ifndef TGB_SKIP_EPI
+      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, cx);
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_remote + (uint32_t)b * 8u);
+    }
+    epi.finish(ew, lane, 0);
+  }
+  tc_fence_before();
+  cluster_sync_all();                           // the peer's shared memory and barriers stay valid until both are done
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -852,12 +1085,27 @@ constexpr int TC_FWD_BN = 256, TC_FWD_STAGES = 4;
 #ifndef TGB_BWD_POLICY_A
 #define TGB_BWD_POLICY_A kPolicyEvictNormal
 #endif
+#ifndef TGB_BWD_POLICY_B
+#define TGB_BWD_POLICY_B kPolicyEvictLast
+#endif
 #ifndef TGB_BWD_BN
 #define TGB_BWD_BN 256
 #endif
 constexpr int TC_BWD_BN = TGB_BWD_BN, TC_BWD_STAGES = TGB_BWD_STAGES, TC_BWD_EPI_WARPS = 8;
 constexpr int TC_RD_STAGES = 4;
-
+// CTA-pair backward kernel (cta_group::2): used from TC_PAIR_MIN_ROWS cells up (smaller problems don't fill 74 pairs)
+#ifndef TGB_BWD_PAIR
+#define TGB_BWD_PAIR 1
+#endif
+#ifndef TGB_PAIR_STAGES
+#define TGB_PAIR_STAGES 4
+#endif
+constexpr int TC_PAIR_STAGES = TGB_PAIR_STAGES, TC_PAIR_MIN_ROWS = 2048;
+// Row tiles per scheduling group of the backward kernel (tile_mn).  Measured at 100k x 10k x 2k, ms per launch:
+// 1: 5.75   4: 5.84   8: 5.86   16: 5.89   37: 7.03 -- many CTAs pulling the same B tile at once hot-spot L2 slices.
+#ifndef TGB_BWD_GROUP
+#define TGB_BWD_GROUP 1
+#endif
 static inline int tc_splits(long long tiles, long long k_total, int min_k) {
   long long s = (2 * 148 + tiles - 1) / tiles;
   const long long max_s = (k_total + min_k - 1) / min_k;
@@ -916,7 +1164,7 @@ static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, size_t p_pla
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
   kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], N, tc_kps(N, splits), tm, tn,
-                                                                         splits, kPolicyEvictNormal, kPolicyEvictNormal, epi);
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
 
@@ -934,7 +1182,7 @@ static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, size_t p_plan
   TcEpiRowDot epi{Sxb, Ke, rpart, N, Sxf};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
   kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], V, tc_kps(V, splits), tm, tn,
-                                                                         splits, kPolicyEvictNormal, kPolicyEvictLast, epi);
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
@@ -950,13 +1198,36 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_
   float* st[3] = {a.Mp, a.mp, a.vp};
   for (int i = 0; i < 3; ++i)
     if (tc_make_map_f32(tc, &me[i], st[i], V, N, a.ld, TcEpiAdam::SW, 32, err, n)) return -2;
+  TcEpiAdam epi{a, N};
+  const int tn = (int)ceil_div(V, TC_BWD_BN);
+#if TGB_BWD_PAIR
+  if (N >= TC_PAIR_MIN_ROWS) {
+    // CTA pairs: 256-row tiles, each CTA stages half of the B tile (box rows = BN / 2)
+    if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN / 2, err, n)) return -2;
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
+    const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
+    if (tc_set_smem(pk, psmem, err, n)) return -2;
+    const int tmp = (int)ceil_div(N, 2 * TC_BM);
+    const long long pair_tiles = (long long)tmp * tn;
+    const unsigned clusters = (unsigned)(pair_tiles < tc.num_sms / 2 ? pair_tiles : tc.num_sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(64 + 32 * TC_BWD_EPI_WARPS); cfg.dynamicSmemBytes = psmem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pk, ma, mb, n_pairs, me[0], me[1], me[2], Ke, tmp, tn, TGB_BWD_GROUP,
+                                       (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, epi);
+    if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
+    return tc_check_launch("tc_gemm_bwd_adam", err, n);
+  }
+#endif
   auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
   const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
   if (tc_set_smem(kern, smem, err, n)) return -2;
-  TcEpiAdam epi{a, N};
-  const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(V, TC_BWD_BN);
+  const int tm = (int)ceil_div(N, TC_BM);
   kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, n_pairs, me[0], me[1], me[2], Ke, Ke, tm, tn, 1,
-                                                                              TGB_BWD_POLICY_A, kPolicyEvictLast, epi);
+                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 
