@@ -426,6 +426,7 @@ struct TcEpiAdam {
 //   BN=256 3x48KB 1-deep + L2 prefetch 1 ahead: 6.36 (chosen)   2 ahead: 6.87   BN=256 2x48KB 2-deep: 7.58
 // The L2->SM operand stream (A is re-read per column tile) competes with 26 B/element of state traffic,
 // so the wider tile (25% fewer operand bytes) and a deeper ring beat a deeper staging pipeline.
+//   CTA pairs (k_gemm_tc_pair, 256x256 per pair, 4x32KB ring): 1-deep 5.75-5.94   2-deep 5.83-5.89   3x32KB ring 2-deep: 6.50
   // leader lane of a group: three bulk tensor loads of sub-tile `c` into staging buffer `b`
   __device__ __forceinline__ void issue_loads(const EpiCtx& cx, int g, int b, int row0, int col) const {
     const uint32_t bar = cx.bars + (uint32_t)(g * 4 + b) * 8u;
