@@ -85,3 +85,26 @@ def test_bad_config_is_rejected_before_touching_the_device():
     assert lib.tgb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"lambda_g1 cannot be 0" in lib.tgb200_last_error()
     assert lib.tgb200_destroy(None) == 0
+
+
+@pytest.mark.gpu
+def test_integration_stub_runs():
+    """The ctypes block of INTEGRATION.md section 3, executed verbatim (only N, V, K, S, G, d, M0 and the library path are
+    supplied from here), must run and agree with the oracle."""
+    import numpy as np
+    from oracle.tangram_oracle import OracleMapper, synthetic_inputs
+    from tangram_b200 import _build, _lib
+    _lib.load()                                               # builds the library if needed
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"## 3\. The ctypes stub.*?```python\n(.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("libtangram_b200.so")', f'ctypes.CDLL({_build.LIB!r})')
+    N, V, K = 300, 70, 40
+    inp = synthetic_inputs(N, V, K, seed=5)
+    M0 = np.random.default_rng(1).standard_normal((N, V))
+    env = dict(N=N, V=V, K=K, S=inp["S"], G=inp["G"], d=inp["d"], M0=M0)
+    block = block.replace("1000", "30")                       # epochs (run / history calls)
+    exec(compile(block, "INTEGRATION.md", "exec"), env)
+    o = OracleMapper(S=inp["S"], G=inp["G"], d=inp["d"], lambda_g1=1.0, lambda_d=1.0, M0=M0.astype(np.float32))
+    ref_out, ref_hist = o.train(30, learning_rate=0.1, print_each=None)
+    assert np.allclose(env["hist"][:, 0], np.array([float(x) for x in ref_hist["total_loss"]]), rtol=1e-4, atol=1e-6)
+    assert np.linalg.norm(env["out"] - ref_out) / np.linalg.norm(ref_out) < 1e-4
