@@ -1014,6 +1014,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct TcContext {
   PFN_encodeTiled encode = nullptr;
   int num_sms = 148;
+  int pair_clusters = -1;   // co-resident 2-CTA clusters of the backward pair kernel (-1 = not queried yet, 0 = unavailable)
 };
 
 static inline int tc_init(TcContext& tc, char* err, size_t n) {
@@ -1204,23 +1205,32 @@ static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_
 #if TGB_BWD_PAIR
   if (N >= TC_PAIR_MIN_ROWS) {
     // CTA pairs: 256-row tiles, each CTA stages half of the B tile (box rows = BN / 2)
-    if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN / 2, err, n)) return -2;
     auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
     const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
     if (tc_set_smem(pk, psmem, err, n)) return -2;
-    const int tmp = (int)ceil_div(N, 2 * TC_BM);
-    const long long pair_tiles = (long long)tmp * tn;
-    const unsigned clusters = (unsigned)(pair_tiles < tc.num_sms / 2 ? pair_tiles : tc.num_sms / 2);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(64 + 32 * TC_BWD_EPI_WARPS); cfg.dynamicSmemBytes = psmem; cfg.stream = s;
+    cfg.blockDim = dim3(64 + 32 * TC_BWD_EPI_WARPS); cfg.dynamicSmemBytes = psmem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, pk, ma, mb, n_pairs, me[0], me[1], me[2], Ke, tmp, tn, TGB_BWD_GROUP,
-                                       (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, epi);
-    if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
-    return tc_check_launch("tc_gemm_bwd_adam", err, n);
+    if (tc.pair_clusters < 0) {   // persistent kernel: never launch more clusters than can be resident at once
+      cfg.gridDim = dim3(tc.num_sms & ~1);
+      int mc = 0;
+      tc.pair_clusters = cudaOccupancyMaxActiveClusters(&mc, pk, &cfg) == cudaSuccess ? mc : 0;
+      (void)cudaGetLastError();
+    }
+    if (tc.pair_clusters > 0) {   // 0: no room for 2-CTA clusters on this device (partitioned GPU) -> single-CTA kernel below
+      if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN / 2, err, n)) return -2;
+      const int tmp = (int)ceil_div(N, 2 * TC_BM);
+      const long long pair_tiles = (long long)tmp * tn;
+      const unsigned clusters = (unsigned)(pair_tiles < tc.pair_clusters ? pair_tiles : tc.pair_clusters);
+      cfg.gridDim = dim3(2 * clusters);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, pk, ma, mb, n_pairs, me[0], me[1], me[2], Ke, tmp, tn, TGB_BWD_GROUP,
+                                         (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, epi);
+      if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
+      return tc_check_launch("tc_gemm_bwd_adam", err, n);
+    }
   }
 #endif
   auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;

@@ -836,12 +836,44 @@ extern "C" int tgb200_project(tgb200_mapper* h, const float* X, int64_t n_cols, 
   if (!h->have_mapping) return fail(TGB200_ERR_STATE, "no mapping set");
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
-  // softmax(M)^T X in fp32, gene columns streamed through in chunks (tangram/utils.py:368)
-  DevBuf<float> Pt;
-  float* P = h->Pf.p;
-  if (h->tcm) { CKS(Pt.alloc((size_t)h->N * h->ld, false)); P = Pt.p; }
-  CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));
+  // softmax(M)^T X, gene columns streamed through in chunks (tangram/utils.py:368)
   const int chunk = 2048;
+  if (h->tcm) {
+    // tensor-core modes: the forward contraction kernel with split-bf16 operands (three planes each, six partial
+    // products, accumulation chains cut at 2048 cells) -- fp32-grade results whatever the training precision was
+    const size_t pplane = (size_t)h->N * h->ld;
+    DevBuf<__nv_bfloat16> Pown, Xb;
+    __nv_bfloat16* Pp = h->Pb.p;                    // bf16x3 mode rewrites its P planes every iteration anyway
+    if (!h->x3) { CKS(Pown.alloc(3 * pplane, false)); Pp = Pown.p; }   // bf16 mode: Pb carries the unnormalised P state
+    CKS(launch_softmax_rows<float>(h, s, (float*)nullptr, 0, nullptr, Split3{Pp, pplane}));
+    const int ldc = (int)round_up(n_cols < chunk ? n_cols : chunk, 64);
+    int splits = tc_forward_splits(h->N, h->V, ldc);
+    { const int c = tc_splits_for_chain(h->N, 2048); if (c > splits) splits = c; }
+    const size_t xplane = (size_t)h->N * ldc, oplane = (size_t)h->V * ldc;
+    DevBuf<float> Xc, Opart, Oc;
+    CKS(Xc.alloc(xplane)); CKS(Xb.alloc(3 * xplane, false)); CKS(Opart.alloc((size_t)splits * oplane, false));
+    if (splits > 1) CKS(Oc.alloc(oplane, false));
+    for (int64_t c0 = 0; c0 < n_cols; c0 += chunk) {
+      const int nc = (int)((n_cols - c0) < chunk ? (n_cols - c0) : chunk);
+      if (nc < ldc) CK(cudaMemsetAsync(Xc.p, 0, xplane * sizeof(float), s));
+      CK(cudaMemcpy2DAsync(Xc.p, (size_t)ldc * sizeof(float), X + c0, (size_t)n_cols * sizeof(float),
+                           (size_t)nc * sizeof(float), h->N, cudaMemcpyDefault, s));
+      k_split3<<<(unsigned)ceil_div(xplane / 4, 256), 256, 0, s>>>(Xc.p, Split3{Xb.p, xplane}, (long long)(xplane / 4));
+      LAUNCH_CHECK("split3");
+      CKS(tc_forward(h->tc, Pp, pplane, Xb.p, xplane, 6, Opart.p, h->N, h->V, ldc, h->ld, splits, s, g_err, sizeof(g_err)));
+      const float* res = Opart.p;
+      if (splits > 1) {
+        k_sum_planes<<<(unsigned)ceil_div(oplane, 256), 256, 0, s>>>(Opart.p, splits, oplane, Oc.p);
+        LAUNCH_CHECK("sum_planes");
+        res = Oc.p;
+      }
+      CK(cudaMemcpy2DAsync(out + c0, (size_t)n_cols * sizeof(float), res, (size_t)ldc * sizeof(float),
+                           (size_t)nc * sizeof(float), h->V, cudaMemcpyDefault, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return TGB200_OK;
+  }
+  CKS(launch_softmax_rows<float>(h, s, h->Pf.p, 0, nullptr));
   const int ldc = (int)round_up(n_cols < chunk ? n_cols : chunk, 4);
   DevBuf<float> Xc, Oc;
   CKS(Xc.alloc((size_t)h->N * ldc)); CKS(Oc.alloc((size_t)h->V * ldc));
@@ -851,7 +883,7 @@ extern "C" int tgb200_project(tgb200_mapper* h, const float* X, int64_t n_cols, 
     CK(cudaMemcpy2DAsync(Xc.p, (size_t)ldc * sizeof(float), X + c0, (size_t)n_cols * sizeof(float),
                          (size_t)nc * sizeof(float), h->N, cudaMemcpyDefault, s));
     GemmArgs g;
-    g.A = P; g.lda = h->ld; g.B = Xc.p; g.ldb = ldc; g.M = h->V; g.N = nc; g.K = h->N;
+    g.A = h->Pf.p; g.lda = h->ld; g.B = Xc.p; g.ldb = ldc; g.M = h->V; g.N = nc; g.K = h->N;
     g.k_per_split = (int)round_up(h->N, 16);
     EpiStorePartial epi{Oc.p, ldc, 0};
     dim3 grid((unsigned)ceil_div(nc, SG_BN), (unsigned)ceil_div(h->V, SG_BM), 1);

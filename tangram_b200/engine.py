@@ -101,6 +101,12 @@ class Engine:
         _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(out), self._s(stream)))
         return out
 
+    def project(self, X, out, stream=None):
+        """out (voxels x n_cols, f32) = softmax(M)^T X; X is (cells x n_cols) f32, host or device memory."""
+        n_cols = int(X.shape[1])
+        _lib.check(self._lib.tgb200_project(self._h, _lib.ptr(X), n_cols, _lib.ptr(out), self._s(stream)))
+        return out
+
     def kernel_launches(self):
         n = ctypes.c_int64()
         _lib.check(self._lib.tgb200_kernel_launches(self._h, ctypes.byref(n)))

@@ -45,6 +45,18 @@ def test_full_size_properties(name, precision):
     eng.get_mapping(M0)
     rs = M0.sum(dim=1)
     assert float((rs - 1).abs().max()) < 2e-5 and float(M0.min()) >= 0.0
+    if name == "c3" and precision == "bf16":
+        # project_genes' GEMM at full size on the device (two column chunks, the second ragged): tensor-core
+        # split-bf16 path vs float64 on the voxel sample
+        X = torch.rand((N, 2304), dtype=torch.float32, device="cuda")
+        out = torch.empty((V, 2304), dtype=torch.float32, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.project(X, out); e1.record(); torch.cuda.synchronize()
+        ref = M0[:, idx].double().t() @ X.double()
+        err = float((out[idx].double() - ref).norm() / ref.norm())
+        print(f"project {N}x{V} mapping onto 2304 genes: {e0.elapsed_time(e1):.1f} ms, rel err vs float64 {err:.2e}")
+        assert err < 1e-5
+        del X, out, ref
     del M0
     # determinism: a second engine on the same inputs reproduces the loss history bit for bit
     eng2, _, _ = _engine(name, precision)

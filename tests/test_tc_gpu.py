@@ -138,3 +138,28 @@ def test_degenerate_and_off_tile_shapes(shape, precision):
     assert rel_fro(out, oo) < tol
     ltol = 5e-3 if precision == "bf16" else 1e-5
     assert np.max(np.abs(np.array([float(x) for x in hist["total_loss"]]) - np.array([float(x) for x in oh["total_loss"]]))) < ltol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_project_multi_chunk_matches_float64(precision):
+    """tgb200_project (project_genes' GEMM, tangram/utils.py:368): more gene columns than one 2048-wide chunk, ragged
+    tail, after a few training steps; every mode returns fp32-grade softmax(M)^T X (the tensor-core modes use the
+    split-bf16 forward kernel), and training continues unperturbed afterwards."""
+    from tangram_b200 import Mapper
+    N, V, K = 2500, 333, 90
+    inp = synthetic_inputs(N, V, K, seed=17)
+    M0 = np.random.default_rng(5).standard_normal((N, V)).astype(np.float32)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_g1=1.0, lambda_d=1.0, M0=M0, precision=precision, device="cuda:0")
+    m = Mapper(**kw)
+    m.train(5, print_each=None)
+    Mcur = m.state()[0].astype(np.float64)
+    P = np.exp(Mcur - Mcur.max(axis=1, keepdims=True)); P /= P.sum(axis=1, keepdims=True)
+    X = np.random.default_rng(6).random((N, 2048 + 77)).astype(np.float32)
+    got = m.project(X)
+    assert got.shape == (V, X.shape[1])
+    assert rel_fro(got, P.T @ X.astype(np.float64)) < 3e-6
+    # projecting must not disturb the optimiser state: 5 + 5 steps == 10 steps of a fresh mapper, bit for bit
+    out_a, hist_a = m.train(5, print_each=None)
+    m2 = Mapper(**kw)
+    out_b, hist_b = m2.train(10, print_each=None)
+    assert np.array_equal(out_a, out_b)
