@@ -192,6 +192,13 @@ TGB200_API int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, doub
  * out_host may be NULL to query the size (*n). */
 TGB200_API int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* out_host, int64_t cap, int64_t* n);
 
+/* Host-binding helpers for the result of Mapper.train (softmax(M).cpu().numpy(), mapping_optimizer.py:406-408): fault in and
+ * page-lock a caller-owned host buffer so that tgb200_get_mapping's device->host copy runs as one DMA at link speed.  Meant to
+ * be called from a host thread WHILE the iterations run (the pages are touched by `threads` worker threads, then registered
+ * with the CUDA driver on `device`); tgb200_host_unpin before the buffer is freed.  Both are optional: an unpinned buffer works, slower. */
+TGB200_API int tgb200_host_pin(void* buf, int64_t bytes, int32_t threads, int32_t device);
+TGB200_API int tgb200_host_unpin(void* buf);
+
 TGB200_API const char* tgb200_last_error(void);
 TGB200_API const char* tgb200_version(void);
 

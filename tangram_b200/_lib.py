@@ -67,6 +67,8 @@ SIGNATURES = {
                                            ctypes.c_int32, _I32]),
     "tgb200_algorithmic_cost": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "tgb200_debug_buffer": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_int64, _I64]),
+    "tgb200_host_pin": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    "tgb200_host_unpin": (ctypes.c_int, [_P]),
     "tgb200_last_error": (ctypes.c_char_p, []),
     "tgb200_version": (ctypes.c_char_p, []),
 }

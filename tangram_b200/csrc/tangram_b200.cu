@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -154,6 +155,31 @@ static bool needs_rowscalars(const tgb200_config& c) {
 }
 
 // ---------------------------------------------------------------------------------------
+extern "C" int tgb200_host_pin(void* buf, int64_t bytes, int32_t threads, int32_t device) {
+  if (!buf || bytes <= 0) return fail(TGB200_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(device));                      // usually a fresh host thread: bind it to the handle's device
+  // first touch with several threads (a fresh 4 GB numpy buffer is a million page faults), then page-lock
+  const size_t page = 4096, n = (size_t)bytes;
+  const int nt = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+  volatile unsigned char* b = static_cast<volatile unsigned char*>(buf);
+  auto touch = [=](size_t lo, size_t hi) { for (size_t o = lo; o < hi; o += page) b[o] = 0; };
+  std::vector<std::thread> pool;
+  const size_t per = ((n + nt - 1) / nt + page - 1) / page * page;
+  for (int t = 1; t < nt; ++t) {
+    const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+    if (lo < n) pool.emplace_back(touch, lo, hi);
+  }
+  touch(0, per < n ? per : n);
+  for (auto& th : pool) th.join();
+  b[n - 1] = 0;
+  CK(cudaHostRegister(buf, n, cudaHostRegisterDefault));
+  return TGB200_OK;
+}
+extern "C" int tgb200_host_unpin(void* buf) {
+  if (!buf) return fail(TGB200_ERR_INVALID, "null argument");
+  CK(cudaHostUnregister(buf));
+  return TGB200_OK;
+}
 extern "C" const char* tgb200_last_error(void) { return g_err; }
 extern "C" const char* tgb200_version(void) { return "tangram_b200 0.1.0 (sm_100a)"; }
 

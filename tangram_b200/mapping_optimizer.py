@@ -57,10 +57,37 @@ def _to_csr(mat, n):
             np.ascontiguousarray(csr.data, dtype=np.float32))
 
 
-def _pinned_empty(shape):
-    """Result buffer for softmax(M).  Plain pageable memory: page-locking 4 GB costs ~1.2 s (cudaHostAlloc), more than
-    the pinned copy saves on a single call (measured, tools/e2e_breakdown.py); the driver's staged pageable copy is used."""
-    return np.empty(shape, dtype=np.float32)
+class _ResultBuffer:
+    """Where softmax(M) lands (mapping_optimizer.py:406-408).  A fresh 4 GB numpy array is a million page faults and a
+    staged pageable copy (~0.7 s at 100k x 10k); so for large results a host thread faults the pages in and page-locks
+    them WHILE the iterations run (tgb200_host_pin), and the final device->host copy is one DMA at link speed.  Results
+    under 256 MB, or a failed registration (locked-memory limit), simply use the pageable path."""
+    MIN_BYTES = 256 << 20
+
+    def __init__(self, lib, shape, device):
+        self.arr = np.empty(shape, dtype=np.float32)
+        self._lib, self._pinned, self._thread = lib, False, None
+        if self.arr.nbytes >= self.MIN_BYTES:
+            import threading
+            self._thread = threading.Thread(target=self._pin, args=(int(device),), daemon=True)
+            self._thread.start()
+
+    def _pin(self, device):
+        import os
+        threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+        self._pinned = self._lib.tgb200_host_pin(_lib.ptr(self.arr), self.arr.nbytes, threads, device) == 0
+
+    def ready(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        return self.arr
+
+    def release(self):
+        self.ready()
+        if self._pinned:
+            self._lib.tgb200_host_unpin(_lib.ptr(self.arr))
+            self._pinned = False
 
 
 def format_terms(row):
@@ -269,7 +296,13 @@ class Mapper:
         _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
         first = first.value
         lr = float(learning_rate)
+        result = _ResultBuffer(self._lib, (self.n_cells, self.n_voxels), self._cfg.device)
+        try:
+            return self._train_loop(num_epochs, lr, print_each, val_each, first, training_history, result)
+        finally:
+            result.release()
 
+    def _train_loop(self, num_epochs, lr, print_each, val_each, first, training_history, result):
         t = 0
         while t < num_epochs:
             if val_each is not None:
@@ -293,7 +326,7 @@ class Mapper:
         for c, key in enumerate(_HIST_KEYS[1:], start=1):
             training_history[key] = [float(x) for x in rows[:, c]]
         self.history_matrix = rows
-        output = _pinned_empty((self.n_cells, self.n_voxels))
+        output = result.ready()
         _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(output), None))
         return output, training_history
 
@@ -406,6 +439,13 @@ class MapperConstrained:
         first = ctypes.c_int64()
         _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
         first = first.value
+        result = _ResultBuffer(self._lib, (self.n_cells, self.n_voxels), self._cfg.device)
+        try:
+            return self._train_loop(num_epochs, learning_rate, print_each, first, keys, result)
+        finally:
+            result.release()
+
+    def _train_loop(self, num_epochs, learning_rate, print_each, first, keys, result):
         t = 0
         while t < num_epochs:
             chunk = min(num_epochs - t, print_each - (t % print_each)) if print_each else num_epochs - t
@@ -423,7 +463,7 @@ class MapperConstrained:
             hist["total_loss"].append("tensor({:.4f}, grad_fn=<AddBackward0>)".format(float(r[0])))     # str(tensor), :630
             for k, v in zip(keys[1:], vals):
                 hist[k].append(str(v))
-        output = _pinned_empty((self.n_cells, self.n_voxels))
+        output = result.ready()
         _lib.check(self._lib.tgb200_get_mapping(self._h, _lib.ptr(output), None))
         F_out = np.empty(self.n_cells, dtype=np.float32)
         _lib.check(self._lib.tgb200_get_filter(self._h, None, _lib.ptr(F_out), None))
