@@ -108,3 +108,26 @@ def test_integration_stub_runs():
     ref_out, ref_hist = o.train(30, learning_rate=0.1, print_each=None)
     assert np.allclose(env["hist"][:, 0], np.array([float(x) for x in ref_hist["total_loss"]]), rtol=1e-4, atol=1e-6)
     assert np.linalg.norm(env["out"] - ref_out) / np.linalg.norm(ref_out) < 1e-4
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_host_pin_without_gpu_reports_an_error_and_leaves_the_buffer_usable():
+    """The result-buffer helper is optional plumbing: with no device it must return an error code (never crash), and
+    Mapper.train's _ResultBuffer then simply keeps the pageable array."""
+    import numpy as np
+    from tangram_b200 import _lib
+    from tangram_b200.mapping_optimizer import _ResultBuffer
+    lib = _lib.load()
+    buf = np.empty(1 << 20, dtype=np.float32)
+    assert lib.tgb200_host_pin(_lib.ptr(buf), buf.nbytes, 4, 0) != 0
+    assert lib.tgb200_last_error()
+    buf[:] = 1.0
+    old = _ResultBuffer.MIN_BYTES
+    _ResultBuffer.MIN_BYTES = 1 << 10
+    try:
+        r = _ResultBuffer(lib, (64, 64), 0)
+        arr = r.ready()
+        assert arr.shape == (64, 64) and not r._pinned
+        r.release()
+    finally:
+        _ResultBuffer.MIN_BYTES = old
