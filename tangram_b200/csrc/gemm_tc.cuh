@@ -98,12 +98,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-#ifdef TGB_PREFETCH_EVICT_LAST
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;"
-               ::"l"(map), "r"(c0), "r"(c1), "l"(kPolicyEvictLast) : "memory");
-#else
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
