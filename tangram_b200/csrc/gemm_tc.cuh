@@ -4,7 +4,8 @@
 //
 //   forward   Y_ext[z] = P[z]^T S_ext[z]        A = P  (MN-major), B = S_ext (MN-major), split over cells
 //   row-dot   r_i = <S_ext_i, (P dY_ext)_i>     A = P  (K-major),  B = dY_ext (MN-major), split over voxels
-//   backward  dP = S_ext dY_ext^T  -> softmax-Jacobian + Adam in the epilogue (A, B K-major)
+//   backward  dP = S_ext dY_ext^T  -> softmax-Jacobian + Adam in the epilogue (A, B K-major); from 2048 cells up
+//             on CTA pairs (k_gemm_tc_pair: tcgen05 cta_group::2, 256-row tiles, half of B staged per CTA)
 //
 // Persistent, warp-specialised kernel: one CTA per SM loops over output tiles.
 //   warp 0      TMA producer: keeps the operand ring full across tile boundaries
