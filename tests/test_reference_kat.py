@@ -36,12 +36,22 @@ def _check(x00, e):
         assert abs(x00 - e) < 0.15 * e                          # 500 chaotic epochs at the 1e-6 level
 
 
+def _check_train_score(X_space, kw, hist):
+    """The reference's test_train_score_match (tests/tangram_test.py:159-211): the mean per-gene cosine between the
+    projected training genes (project_genes, tangram/utils.py:368) and the measured ones (compare_spatial_geneexp,
+    tangram/utils.py:412-428) equals the last main_loss of the training history to three decimals."""
+    A, B = np.asarray(X_space, dtype=np.float64), np.asarray(kw["G"], dtype=np.float64)
+    cos = (A * B).sum(axis=0) / (np.linalg.norm(A, axis=0) * np.linalg.norm(B, axis=0))
+    assert abs(cos.mean() * kw["lambda_g1"] - float(hist["main_loss"][-1])) < 5e-4
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_oracle_reproduces_reference_known_answers(case):
     kw, e = _inputs(case)
     out, hist = OracleMapper(**kw).train(500, print_each=None)
     assert out.shape == (18, 9852)
     _check(out[0, 0], e)
+    _check_train_score(out.astype(np.float64).T @ kw["S"].astype(np.float64), kw, hist)
 
 
 @pytest.mark.gpu
@@ -50,8 +60,12 @@ def test_oracle_reproduces_reference_known_answers(case):
 def test_cuda_reproduces_reference_known_answers(case, precision):
     from tangram_b200 import Mapper
     kw, e = _inputs(case)
-    out, hist = Mapper(device="cuda:0", precision=precision, **kw).train(500, print_each=None)
+    m = Mapper(device="cuda:0", precision=precision, **kw)
+    out, hist = m.train(500, print_each=None)
     _check(out[0, 0], e)
+    X_space = m.project(kw["S"])                               # project_genes' GEMM on the device
+    assert np.allclose(X_space, out.astype(np.float64).T @ kw["S"].astype(np.float64), rtol=2e-5, atol=1e-7)
+    _check_train_score(X_space, kw, hist)
 
 
 @pytest.mark.skipif(not (os.path.exists(H5_SC) and os.path.exists(H5_SP)), reason="reference data not present (GPU box)")
