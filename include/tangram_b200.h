@@ -136,6 +136,9 @@ TGB200_API int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indp
 TGB200_API int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* stream);
 /* Device-side N(0,1) init (Philox) for throughput runs; NOT bit-compatible with :150. */
 TGB200_API int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream);
+/* Same for a cell-sharded handle: `first_row` is the global index of this handle's first cell, so the draw of a
+ * cell does not depend on how the cells are sharded over ranks (tgb200_init_mapping_normal == first_row 0). */
+TGB200_API int tgb200_init_mapping_normal_rows(tgb200_mapper* h, uint64_t seed, int64_t first_row, void* stream);
 
 /* Constrained mode: initial filter logits F0 (n_cells, host or device; the reference draws them at :490).
  * Resets the filter's Adam state. */

@@ -25,7 +25,7 @@ import torch
 EPS_COS = 1e-8  # torch.nn.functional.cosine_similarity default eps
 
 
-def _as_op(mat, dtype):
+def _as_op(mat, dtype, device="cpu"):
     """Dense ndarray / scipy sparse / torch tensor -> (matmul, rmatmul) closures.
 
     The reference receives dense V x V matrices (mapping_optimizer.py:125-141).
@@ -40,16 +40,16 @@ def _as_op(mat, dtype):
             torch.as_tensor(csr.indices, dtype=torch.int64),
             torch.as_tensor(csr.data, dtype=dtype),
             size=csr.shape,
-        )
+        ).to(device)
         csr_t = csr.T.tocsr()
         tt = torch.sparse_csr_tensor(
             torch.as_tensor(csr_t.indptr, dtype=torch.int64),
             torch.as_tensor(csr_t.indices, dtype=torch.int64),
             torch.as_tensor(csr_t.data, dtype=dtype),
             size=csr_t.shape,
-        )
+        ).to(device)
         return (lambda x: torch.sparse.mm(t, x)), (lambda x: torch.sparse.mm(tt, x))
-    dense = torch.as_tensor(np.asarray(mat), dtype=dtype)
+    dense = torch.as_tensor(np.asarray(mat), dtype=dtype).to(device)
     return (lambda x: dense @ x), (lambda x: dense.t() @ x)
 
 
@@ -103,28 +103,29 @@ class OracleMapper:
             # mapping_optimizer.py:173-185 -- out of scope
             raise NotImplementedError("Moran / Geary terms are outside the hot-path scope")
         self.dtype = dtype
+        self.device = device      # "cpu" (default); the GPU tests run this same restatement on "cuda" at BASELINE's full sizes
         self.random_state = random_state
-        S = torch.as_tensor(np.asarray(S), dtype=torch.float32)
-        G = torch.as_tensor(np.asarray(G), dtype=torch.float32)
+
+        def _t(x):                # f32 first (the reference's cast, :83-84), then the oracle's working dtype
+            x = x.detach() if hasattr(x, "detach") else np.asarray(x)
+            return torch.as_tensor(x, dtype=torch.float32).to(device=device, dtype=dtype)
+        S, G = _t(S), _t(G)
         # mapping_optimizer.py:87-92: train subset (val subset is never used, :321-322)
         if train_genes_idx is not None:
             S = S[:, train_genes_idx]
             G = G[:, train_genes_idx]
-        self.S = S.to(dtype).contiguous()
-        self.G = G.to(dtype).contiguous()
+        self.S = S.contiguous()
+        self.G = G.contiguous()
         self.lam = dict(
             g1=lambda_g1, d=lambda_d, g2=lambda_g2, r=lambda_r, l1=lambda_l1, l2=lambda_l2,
             nb=lambda_neighborhood_g1, ct=lambda_ct_islands, go=lambda_getis_ord,
         )
-        self.d = None if d is None else torch.as_tensor(np.asarray(d), dtype=torch.float32).to(dtype)
-        self.d_source = (
-            None if d_source is None
-            else torch.as_tensor(np.asarray(d_source), dtype=torch.float32).to(dtype)
-        )
-        self.W = _as_op(voxel_weights, dtype)
-        self.F = _as_op(neighborhood_filter, dtype)
-        self.A = _as_op(spatial_weights, dtype)
-        self.E = None if ct_encode is None else torch.as_tensor(np.asarray(ct_encode), dtype=torch.float32).to(dtype)
+        self.d = None if d is None else _t(d)
+        self.d_source = None if d_source is None else _t(d_source)
+        self.W = _as_op(voxel_weights, dtype, device)
+        self.F = _as_op(neighborhood_filter, dtype, device)
+        self.A = _as_op(spatial_weights, dtype, device)
+        self.E = None if ct_encode is None else _t(ct_encode)
 
         # constants (mapping_optimizer.py:144, :170-171, :236)
         if self.lam["go"] > 0:
@@ -139,7 +140,7 @@ class OracleMapper:
             if self.random_state:
                 np.random.seed(seed=self.random_state)
             M0 = np.random.normal(0, 1, (self.S.shape[0], self.G.shape[0]))
-        self.M = torch.as_tensor(np.asarray(M0), dtype=torch.float32).to(dtype).clone()
+        self.M = _t(M0).clone()
         self.m = torch.zeros_like(self.M)
         self.v = torch.zeros_like(self.M)
         self.t = 0
@@ -301,7 +302,7 @@ class OracleMapper:
                 vals = self.val_terms()
                 for k, x in zip(val_keys, vals):
                     history[k].append(x)
-        out = torch.softmax(self.M, dim=1).to(torch.float32).numpy()
+        out = torch.softmax(self.M, dim=1).to(torch.float32).cpu().numpy()
         return out, history
 
     def val_terms(self):

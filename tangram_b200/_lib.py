@@ -49,6 +49,7 @@ SIGNATURES = {
     "tgb200_set_graph": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, ctypes.c_int64, _P]),
     "tgb200_set_mapping": (ctypes.c_int, [_P, _P, _P]),
     "tgb200_init_mapping_normal": (ctypes.c_int, [_P, ctypes.c_uint64, _P]),
+    "tgb200_init_mapping_normal_rows": (ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int64, _P]),
     "tgb200_set_filter": (ctypes.c_int, [_P, _P, _P]),
     "tgb200_get_filter": (ctypes.c_int, [_P, _P, _P, _P]),
     "tgb200_run": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_float, _P]),

@@ -84,6 +84,12 @@ __device__ __forceinline__ void store_row_words(void* dst, const uint32_t (&w)[W
   for (int u = 0; u < WORDS / 8; ++u) stg256(reinterpret_cast<uint8_t*>(dst) + 32 * u, &w[8 * u]);
   if (WORDS % 8) reinterpret_cast<uint4*>(dst)[WORDS / 4 - 1] = make_uint4(w[WORDS - 4], w[WORDS - 3], w[WORDS - 2], w[WORDS - 1]);
 }
+// one full 32-byte sector per thread, read-only path (sm_100+: LDG.256)
+__device__ __forceinline__ void ldg256(const void* src, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(src));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
@@ -329,6 +335,67 @@ struct TcEpiRowDot {
       }
     }
     if (row < M) rpart[((size_t)t.split * t.tiles_n + t.tile_n) * M + row] = acc;
+  }
+};
+
+// Store-only backward epilogue (bf16 throughput mode, "staged" backward): dP = S_ext dY_ext^T leaves the kernel as
+// bf16, centred per row on the previous iteration's row-dot (dq_ij = bf16(dP_ij - c_i): the softmax-Jacobian only sees
+// dP_ij - r_i, so the bf16 rounding is relative to the deviation from the row mean, not to dP itself), and the same
+// epilogue accumulates this iteration's row-dot partials r'_i = sum_j Pt_ij dq_ij from the ROUNDED values (so that
+// sum_j g_ij = 0 holds for what the streaming Adam kernel consumes).  Thread = row (TMEM lane), one 32-byte sector of
+// Pt in and one of dq out per 16 columns; the Pt segment of the tile is prefetched into L2 before the wait on the MMAs.
+struct TcEpiDpStore {
+  __nv_bfloat16* dq; const __nv_bfloat16* Pt; int ld;     // both [rows][ld]
+  const float* center;                                    // c_i (per row)
+  float* rpart;                                           // [tiles_n * 2][M]
+  int M;
+  static constexpr int kStagingBytes = 0;
+  template <int BN, int NW>
+  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx&) const {
+    static_assert(NW == 8, "two warps per TMEM lane quarter");
+    const int row = t.m0 + q * 32 + lane, col = t.n0 + (ew >> 2) * (BN / 2);
+    if (row < M) {
+      const __nv_bfloat16* src = Pt + (size_t)row * ld + col;
+#pragma unroll
+      for (int b = 0; b < BN / 2; b += 64)      // 128-byte lines of this thread's row segment
+        if (col + b < ld) prefetch_l2(src + b);
+    }
+  }
+  __device__ __forceinline__ void finish(int, int, int) const {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx&) const {
+    static_assert(NW == 8, "two warps per TMEM lane quarter");
+    constexpr int NCH = BN / 2 / 16;
+    const int part = ew >> 2;
+    const int row = t.m0 + q * 32 + lane;
+    const int cbase = t.n0 + part * (BN / 2);
+    const bool live = row < M;
+    const float c = live ? center[row] : 0.f;
+    const __nv_bfloat16* prow = Pt + (size_t)row * ld;
+    __nv_bfloat16* drow = dq + (size_t)row * ld;
+    uint32_t pw[2][8];
+    if (live && cbase < ld) ldg256(prow + cbase, pw[0]);
+    float racc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int col0 = cbase + i * 16;
+      if (i + 1 < NCH && live && col0 + 16 < ld) ldg256(prow + col0 + 16, pw[(i + 1) & 1]);
+      float v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), v);
+      if (live && col0 < ld) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __nv_bfloat162 d2 = __floats2bfloat162_rn(v[2 * e] - c, v[2 * e + 1] - c);
+          const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[i & 1][e]);
+          racc = fmaf(__low2float(p2), __low2float(d2), racc);
+          racc = fmaf(__high2float(p2), __high2float(d2), racc);
+          w[e] = *reinterpret_cast<const uint32_t*>(&d2);
+        }
+        stg256(drow + col0, w);
+      }
+    }
+    if (live) rpart[((size_t)t.tile_n * 2 + part) * M + row] = racc;
   }
 };
 
@@ -665,7 +732,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
           const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
           const __grid_constant__ CUtensorMap map_e2,
           int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, int group_m, uint64_t policy_a,
-          uint64_t policy_b, const Epi epi) {
+          uint64_t policy_b, int tm_off, const Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
   using TileB = OperandTile<B_KMAJOR, BN>;
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
@@ -711,7 +778,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
         const int z = w / (tiles_n * tiles_m);
         int tm_i, tn_i;
         tile_mn(w - z * tiles_n * tiles_m, tiles_m, tiles_n, group_m, tm_i, tn_i);
-        const int n0 = tn_i * BN, m0 = tm_i * TC_BM;
+        const int n0 = tn_i * BN, m0 = (tm_off + tm_i) * TC_BM;
         const int k_begin = z * k_per_split;
         const int k_end = min(k_total, k_begin + k_per_split);
         const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
@@ -779,7 +846,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
       tile_mn(w - t.split * tiles_n * tiles_m, tiles_m, tiles_n, group_m, tm_i, t.tile_n);
       t.tiles_n = tiles_n;
       t.n0 = t.tile_n * BN;
-      t.m0 = tm_i * TC_BM;
+      t.m0 = (tm_off + tm_i) * TC_BM;
       const int b = it & 1;
 #ifndef TGB_SKIP_EPI
       epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
@@ -862,7 +929,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
                const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                const __grid_constant__ CUtensorMap map_e2, int k_total, int tiles_m, int tiles_n, int group_m,
-               uint64_t policy_a, uint64_t policy_b, const Epi epi) {
+               uint64_t policy_a, uint64_t policy_b, int tm_off, const Epi epi) {
   using TileA = OperandTile<true, TC_BM>;         // this CTA's 128 rows
   using TileB = OperandTile<true, BN / 2>;        // this CTA's half of the B tile
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
@@ -915,7 +982,7 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
         int tm_i, tn_i;
         tile_mn(w, tiles_m, tiles_n, group_m, tm_i, tn_i);
         const int n0 = tn_i * BN + (int)rank * (BN / 2);
-        const int m0 = tm_i * (2 * TC_BM) + (int)rank * TC_BM;
+        const int m0 = (tm_off + tm_i) * (2 * TC_BM) + (int)rank * TC_BM;
         for (int pr = 6 - n_pairs; pr < 6; ++pr) {
           const CUtensorMap* ma = &maps_a.m[kPairA[pr]];
           const CUtensorMap* mb = &maps_b.m[kPairB[pr]];
@@ -980,7 +1047,7 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
       tile_mn(w, tiles_m, tiles_n, group_m, tm_i, t.tile_n);
       t.tiles_n = tiles_n;
       t.n0 = t.tile_n * BN;
-      t.m0 = tm_i * (2 * TC_BM) + (int)rank * TC_BM;
+      t.m0 = (tm_off + tm_i) * (2 * TC_BM) + (int)rank * TC_BM;
       t.split = 0;
       const int b = it & 1;
 #ifndef TGB_SKIP_EPI
@@ -1011,6 +1078,9 @@ struct TcContext {
   PFN_encodeTiled encode = nullptr;
   int num_sms = 148;
   int pair_clusters = -1;   // co-resident 2-CTA clusters of the backward pair kernel (-1 = not queried yet, 0 = unavailable)
+  int dp_clusters = -1;     // same for the store-only backward kernel
+  const void* smem_fn[16] = {};   // kernels whose dynamic shared-memory limit this handle has already raised
+  int smem_bytes[16] = {};
 };
 
 static inline int tc_init(TcContext& tc, char* err, size_t n) {
@@ -1064,10 +1134,18 @@ static inline int tc_make_map_f32(TcContext& tc, CUtensorMap* map, const void* b
   return 0;
 }
 
+// cudaFuncSetAttribute once per (handle, kernel): it is a driver call, not something to repeat on every launch
 template <class Kern>
-static inline int tc_set_smem(Kern kern, int bytes, char* err, size_t n) {
+static inline int tc_set_smem(TcContext& tc, Kern kern, int bytes, char* err, size_t n) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  int slot = -1;
+  for (int i = 0; i < 16; ++i) {
+    if (tc.smem_fn[i] == key) { if (tc.smem_bytes[i] == bytes) return 0; slot = i; break; }
+    if (tc.smem_fn[i] == nullptr && slot < 0) slot = i;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) { snprintf(err, n, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e)); return -2; }
+  if (slot >= 0) { tc.smem_fn[slot] = key; tc.smem_bytes[slot] = bytes; }
   return 0;
 }
 static inline int tc_check_launch(const char* name, char* err, size_t n) {
@@ -1099,6 +1177,11 @@ constexpr int TC_RD_STAGES = 4;
 #define TGB_PAIR_STAGES 4
 #endif
 constexpr int TC_PAIR_STAGES = TGB_PAIR_STAGES, TC_PAIR_MIN_ROWS = 2048;
+// store-only backward (staged dP): no epilogue staging in shared memory, so the operand ring can be deeper
+#ifndef TGB_DP_STAGES
+#define TGB_DP_STAGES 6
+#endif
+constexpr int TC_DP_STAGES = TGB_DP_STAGES, TC_DP_SINGLE_STAGES = 4;
 // Row tiles per scheduling group of the backward kernel (tile_mn).  Measured at 100k x 10k x 2k, ms per launch:
 // 1: 5.75   4: 5.84   8: 5.86   16: 5.89   37: 7.03 -- many CTAs pulling the same B tile at once hot-spot L2 slices.
 #ifndef TGB_BWD_GROUP
@@ -1148,94 +1231,178 @@ static inline int tc_make_maps(TcContext& tc, TcMaps* maps, const __nv_bfloat16*
   return 0;
 }
 
+// The tensor maps of one contraction over fixed device buffers.  cuTensorMapEncodeTiled is a driver call: the handle
+// encodes each plan once (the buffers never move) instead of on every launch.
+struct TcPlan {
+  TcMaps a, b;
+  CUtensorMap e[3];
+  bool pair = false;        // b is encoded for the CTA-pair kernel (half-tile boxes)
+  bool ready = false;
+};
+
 // Y_ext[z] (V x Ke) = P[cells of split z]^T S_ext[...]
+static inline int tc_forward_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* Sx,
+                                  size_t s_plane, int planes, int N, int V, int Ke, int ld, char* err, size_t n) {
+  if (tc_make_maps(tc, &pl.a, P, p_plane, planes, V, N, ld, 64, 64, err, n)) return -2;      // A: MN-major (voxels contiguous), rows = cells
+  if (tc_make_maps(tc, &pl.b, Sx, s_plane, planes, Ke, N, Ke, 64, 64, err, n)) return -2;    // B: MN-major (genes contiguous), rows = cells
+  pl.ready = true;
+  return 0;
+}
+static inline int tc_forward_launch(TcContext& tc, const TcPlan& pl, int n_pairs, float* out, int N, int V, int Ke, int splits,
+                                    cudaStream_t s, char* err, size_t n) {
+  auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
+  const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
+  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
+  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
+  const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], N, tc_kps(N, splits), tm, tn,
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, epi);
+  return tc_check_launch("tc_gemm_fwd", err, n);
+}
+// one-shot variant for temporary operands (tgb200_project)
 static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* Sx, size_t s_plane,
                              int n_pairs, float* out, int N, int V, int Ke, int ld, int splits, cudaStream_t s, char* err,
                              size_t n) {
-  TcMaps ma, mb;
-  const int planes = n_pairs > 1 ? 3 : 1;
-  if (tc_make_maps(tc, &ma, P, p_plane, planes, V, N, ld, 64, 64, err, n)) return -2;      // A: MN-major (voxels contiguous), rows = cells
-  if (tc_make_maps(tc, &mb, Sx, s_plane, planes, Ke, N, Ke, 64, 64, err, n)) return -2;    // B: MN-major (genes contiguous), rows = cells
-  auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
-  const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
-  if (tc_set_smem(kern, smem, err, n)) return -2;
-  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
-  const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], N, tc_kps(N, splits), tm, tn,
-                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, epi);
-  return tc_check_launch("tc_gemm_fwd", err, n);
+  TcPlan pl;
+  if (tc_forward_plan(tc, pl, P, p_plane, Sx, s_plane, n_pairs > 1 ? 3 : 1, N, V, Ke, ld, err, n)) return -2;
+  return tc_forward_launch(tc, pl, n_pairs, out, N, V, Ke, splits, s, err, n);
 }
 
 // rpart[(z * ntiles_n + tn)][i] = sum over the tile's genes of (P dY_ext)_ik S_ext_ik
-static inline int tc_rowdot(TcContext& tc, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* dYb, size_t dy_plane,
-                            int n_pairs, const __nv_bfloat16* Sxb, const float* Sxf, float* rpart, int N, int V, int Ke, int ld,
-                            int splits, cudaStream_t s, char* err, size_t n) {
-  TcMaps ma, mb;
-  const int planes = n_pairs > 1 ? 3 : 1;
-  if (tc_make_maps(tc, &ma, P, p_plane, planes, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
-  if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, 64, err, n)) return -2;  // B: MN-major (genes contiguous), rows = voxels
+static inline int tc_rowdot_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* dYb,
+                                 size_t dy_plane, int planes, int N, int V, int Ke, int ld, char* err, size_t n) {
+  if (tc_make_maps(tc, &pl.a, P, p_plane, planes, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
+  if (tc_make_maps(tc, &pl.b, dYb, dy_plane, planes, Ke, V, Ke, 64, 64, err, n)) return -2;  // B: MN-major (genes contiguous), rows = voxels
+  pl.ready = true;
+  return 0;
+}
+static inline int tc_rowdot_launch(TcContext& tc, const TcPlan& pl, int n_pairs, const __nv_bfloat16* Sxb, const float* Sxf,
+                                   float* rpart, int N, int V, int Ke, int splits, cudaStream_t s, char* err, size_t n) {
   auto kern = k_gemm_tc<true, false, TC_RDOT_BN, TC_RD_STAGES, 4, TcEpiRowDot>;
   const int smem = TC_RD_STAGES * (TC_BM + TC_RDOT_BN) * TC_BK * 2 + 1024;
-  if (tc_set_smem(kern, smem, err, n)) return -2;
+  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   TcEpiRowDot epi{Sxb, Ke, rpart, N, Sxf};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(ma, mb, n_pairs, ma.m[0], ma.m[0], ma.m[0], V, tc_kps(V, splits), tm, tn,
-                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], V, tc_kps(V, splits), tm, tn,
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, 0, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
-// dP = S_ext dY_ext^T fused with the softmax-Jacobian, Adam, and (bf16 mode) next iteration's P
-static inline int tc_backward(TcContext& tc, const __nv_bfloat16* Sxb, size_t s_plane, const __nv_bfloat16* dYb, size_t dy_plane,
-                              int n_pairs, const TcAdamArgs& a, int N, int V, int Ke, cudaStream_t s, char* err, size_t n) {
-  TcMaps ma, mb;
-  const int planes = n_pairs > 1 ? 3 : 1;
-  if (tc_make_maps(tc, &ma, Sxb, s_plane, planes, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
-  if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN, err, n)) return -2; // B: K-major, rows = voxels
+// number of co-resident 2-CTA clusters of a pair kernel (persistent: never launch more), 0 = unavailable
+template <class Kern>
+static inline int tc_pair_clusters(TcContext& tc, Kern pk, int threads, int smem, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(tc.num_sms & ~1);
+  int mc = 0;
+  const int r = cudaOccupancyMaxActiveClusters(&mc, pk, &cfg) == cudaSuccess ? mc : 0;
+  (void)cudaGetLastError();
+  return r;
+}
+template <class Kern, class... Args>
+static inline cudaError_t tc_launch_pair(Kern pk, unsigned clusters, int threads, int smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(2 * clusters);
+  return cudaLaunchKernelEx(&cfg, pk, args...);
+}
+
+// dP = S_ext dY_ext^T fused with the softmax-Jacobian and Adam (parity mode; the bf16 mode before the staged backward)
+static inline int tc_backward_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* Sxb, size_t s_plane, const __nv_bfloat16* dYb,
+                                   size_t dy_plane, int planes, const TcAdamArgs& a, int N, int V, int Ke, cudaStream_t s,
+                                   char* err, size_t n) {
+  if (tc_make_maps(tc, &pl.a, Sxb, s_plane, planes, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
   // state arrays as fp32 2D tensors [N][V] (pitch ld): 32 x 32 boxes, 128B swizzle; stores clip at V / N
-  CUtensorMap me[3];
   float* st[3] = {a.Mp, a.mp, a.vp};
   for (int i = 0; i < 3; ++i)
-    if (tc_make_map_f32(tc, &me[i], st[i], V, N, a.ld, TcEpiAdam::SW, 32, err, n)) return -2;
-  TcEpiAdam epi{a, N};
-  const int tn = (int)ceil_div(V, TC_BWD_BN);
+    if (tc_make_map_f32(tc, &pl.e[i], st[i], V, N, a.ld, TcEpiAdam::SW, 32, err, n)) return -2;
+  pl.pair = false;
 #if TGB_BWD_PAIR
   if (N >= TC_PAIR_MIN_ROWS) {
-    // CTA pairs: 256-row tiles, each CTA stages half of the B tile (box rows = BN / 2)
     auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
     const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
-    if (tc_set_smem(pk, psmem, err, n)) return -2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(64 + 32 * TC_BWD_EPI_WARPS); cfg.dynamicSmemBytes = psmem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (tc.pair_clusters < 0) {   // persistent kernel: never launch more clusters than can be resident at once
-      cfg.gridDim = dim3(tc.num_sms & ~1);
-      int mc = 0;
-      tc.pair_clusters = cudaOccupancyMaxActiveClusters(&mc, pk, &cfg) == cudaSuccess ? mc : 0;
-      (void)cudaGetLastError();
-    }
-    if (tc.pair_clusters > 0) {   // 0: no room for 2-CTA clusters on this device (partitioned GPU) -> single-CTA kernel below
-      if (tc_make_maps(tc, &mb, dYb, dy_plane, planes, Ke, V, Ke, 64, TC_BWD_BN / 2, err, n)) return -2;
-      const int tmp = (int)ceil_div(N, 2 * TC_BM);
-      const long long pair_tiles = (long long)tmp * tn;
-      const unsigned clusters = (unsigned)(pair_tiles < tc.pair_clusters ? pair_tiles : tc.pair_clusters);
-      cfg.gridDim = dim3(2 * clusters);
-      cudaError_t e = cudaLaunchKernelEx(&cfg, pk, ma, mb, n_pairs, me[0], me[1], me[2], Ke, tmp, tn, TGB_BWD_GROUP,
-                                         (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, epi);
-      if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
-      return tc_check_launch("tc_gemm_bwd_adam", err, n);
-    }
+    if (tc_set_smem(tc, pk, psmem, err, n)) return -2;
+    if (tc.pair_clusters < 0) tc.pair_clusters = tc_pair_clusters(tc, pk, 64 + 32 * TC_BWD_EPI_WARPS, psmem, s);
+    pl.pair = tc.pair_clusters > 0;   // 0: no room for 2-CTA clusters on this device (partitioned GPU) -> single-CTA kernel
   }
 #endif
+  // B: K-major, rows = voxels; CTA pairs stage half of the B tile per CTA (box rows = BN / 2)
+  if (tc_make_maps(tc, &pl.b, dYb, dy_plane, planes, Ke, V, Ke, 64, pl.pair ? TC_BWD_BN / 2 : TC_BWD_BN, err, n)) return -2;
+  pl.ready = true;
+  return 0;
+}
+static inline int tc_backward_launch(TcContext& tc, const TcPlan& pl, int n_pairs, const TcAdamArgs& a, int N, int V, int Ke,
+                                     cudaStream_t s, char* err, size_t n) {
+  TcEpiAdam epi{a, N};
+  const int tn = (int)ceil_div(V, TC_BWD_BN);
+  if (pl.pair) {
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
+    const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
+    const int tmp = (int)ceil_div(N, 2 * TC_BM);
+    const long long pair_tiles = (long long)tmp * tn;
+    const unsigned clusters = (unsigned)(pair_tiles < tc.pair_clusters ? pair_tiles : tc.pair_clusters);
+    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * TC_BWD_EPI_WARPS, psmem, s, pl.a, pl.b, n_pairs, pl.e[0], pl.e[1], pl.e[2], Ke,
+                                   tmp, tn, TGB_BWD_GROUP, (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, 0, epi);
+    if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
+    return tc_check_launch("tc_gemm_bwd_adam", err, n);
+  }
   auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
   const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
-  if (tc_set_smem(kern, smem, err, n)) return -2;
+  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   const int tm = (int)ceil_div(N, TC_BM);
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(ma, mb, n_pairs, me[0], me[1], me[2], Ke, Ke, tm, tn, 1,
-                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(pl.a, pl.b, n_pairs, pl.e[0], pl.e[1], pl.e[2], Ke, Ke, tm, tn, 1,
+                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, 0, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
+}
+
+// Staged backward (bf16 throughput mode): dq = bf16(S_ext dY_ext^T - centre) to HBM + row-dot partials; the update itself
+// is the streaming kernel k_adam_rows.  Rows [row0, row1) only (row0 a multiple of 256): the host pipelines row chunks.
+static inline int tc_dpstore_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* Sxb, const __nv_bfloat16* dYb, int N, int V,
+                                  int Ke, cudaStream_t s, char* err, size_t n) {
+  if (tc_make_maps(tc, &pl.a, Sxb, 0, 1, Ke, N, Ke, 64, TC_BM, err, n)) return -2;
+  pl.pair = false;
+#if TGB_BWD_PAIR
+  if (N >= TC_PAIR_MIN_ROWS) {
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, 8, TcEpiDpStore>;
+    const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
+    if (tc_set_smem(tc, pk, psmem, err, n)) return -2;
+    if (tc.dp_clusters < 0) tc.dp_clusters = tc_pair_clusters(tc, pk, 64 + 32 * 8, psmem, s);
+    pl.pair = tc.dp_clusters > 0;
+  }
+#endif
+  if (tc_make_maps(tc, &pl.b, dYb, 0, 1, Ke, V, Ke, 64, pl.pair ? TC_BWD_BN / 2 : TC_BWD_BN, err, n)) return -2;
+  pl.ready = true;
+  return 0;
+}
+static inline int tc_dpstore_launch(TcContext& tc, const TcPlan& pl, const TcEpiDpStore& epi, int row0, int row1, int V, int Ke,
+                                    cudaStream_t s, char* err, size_t n) {
+  const int tn = (int)ceil_div(V, TC_BWD_BN);
+  if (pl.pair) {
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, 8, TcEpiDpStore>;
+    const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
+    const int tm0 = row0 / (2 * TC_BM), tmp = (int)ceil_div(row1, 2 * TC_BM) - tm0;
+    const long long pair_tiles = (long long)tmp * tn;
+    const unsigned clusters = (unsigned)(pair_tiles < tc.dp_clusters ? pair_tiles : tc.dp_clusters);
+    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * 8, psmem, s, pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, tmp, tn, 1,
+                                   (uint64_t)kPolicyEvictNormal, (uint64_t)kPolicyEvictLast, tm0, epi);
+    if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_dp (pair): %s", cudaGetErrorString(e)); return -2; }
+    return tc_check_launch("tc_gemm_bwd_dp", err, n);
+  }
+  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_DP_SINGLE_STAGES, 8, TcEpiDpStore>;
+  const int smem = TC_DP_SINGLE_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + 1024;
+  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
+  const int tm0 = row0 / TC_BM, tm = (int)ceil_div(row1, TC_BM) - tm0;
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 8, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, Ke, tm, tn, 1, 1,
+                                                                 kPolicyEvictNormal, kPolicyEvictLast, tm0, epi);
+  return tc_check_launch("tc_gemm_bwd_dp", err, n);
 }
 
 }  // namespace tgb

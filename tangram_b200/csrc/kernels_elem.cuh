@@ -639,13 +639,14 @@ __global__ void k_f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __re
 }
 // M0 ~ N(0,1) on device (Philox4x32-10), pad columns zero.  Throughput runs only; the
 // reference draw (:150) is a host MT19937 float64 draw and is uploaded via set_mapping.
-__global__ void k_init_normal(float* __restrict__ M, int rows, int V, int ld, unsigned long long seed) {
+__global__ void k_init_normal(float* __restrict__ M, int rows, int V, int ld, unsigned long long seed, long long first_row) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 each
   const int nvec = ld >> 2;
   if (q >= (long long)rows * nvec) return;
   const int r = (int)(q / nvec), c = (int)(q % nvec) * 4;
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)q, 0, &st);
+  // subsequence = global float4 index: the draw does not depend on how the cells are sharded over ranks
+  curand_init(seed, (unsigned long long)(q + first_row * nvec), 0, &st);
   float4 n = curand_normal4(&st);
   if (c + 0 >= V) n.x = 0.f;
   if (c + 1 >= V) n.y = 0.f;
@@ -709,6 +710,24 @@ __global__ void k_rowdot_finalize_tc(const float* __restrict__ rpart, int nparts
   for (int p = 0; p < nparts; ++p) s += rpart[(size_t)p * n_rows + i];
   s *= inv_zt[i];
   r[i] = s;
+  rowc[i] = make_float4(lseT[i], s, stats[i].h, 0.f);
+}
+
+// Staged backward: the store-only contraction left partials of r'_i = sum_j Pt_ij (dP_ij - c_i); with P = Pt / zt:
+//   rowc_i = (lseT_i, r'_i / zt_i, h_i, 0) for the streaming Adam kernel,  r_i = c_i + r'_i / zt_i  (full row-dot),
+// and r_i becomes the centre of the next iteration's dq.  Rows [row0, row1).
+__global__ void k_rowdot_finalize_staged(const float* __restrict__ rpart, int nparts, int n_rows, int row0, int row1,
+                                         const float* __restrict__ lseT, const float* __restrict__ inv_zt,
+                                         const RowStat* __restrict__ stats, float* __restrict__ center,
+                                         float* __restrict__ r, float4* __restrict__ rowc) {
+  const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= row1) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += rpart[(size_t)p * n_rows + i];
+  s *= inv_zt[i];
+  const float full = center[i] + s;
+  r[i] = full;
+  center[i] = full;
   rowc[i] = make_float4(lseT[i], s, stats[i].h, 0.f);
 }
 

@@ -15,6 +15,7 @@
 #include "kernels_elem.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "adam_rows.cuh"
 
 using namespace tgb;
 
@@ -121,7 +122,13 @@ struct tgb200_mapper {
   bool in_step = false;
   int64_t launches = 0;
   KernelTimer* timer = nullptr;
-  TcContext tc;                 // tensor maps etc. for the tcgen05 path
+  TcContext tc;                 // driver entry points etc. for the tcgen05 path
+  TcPlan plan_fwd, plan_rd, plan_bwd, plan_dp;   // tensor maps of the contractions, encoded once (the buffers never move)
+  // staged backward (bf16 mode): store-only contraction -> bf16 dq = dP - centre in HBM -> streaming Adam kernel;
+  // two contractions per iteration instead of three (no separate row-dot GEMM)
+  bool staged = false;
+  DevBuf<__nv_bfloat16> dq;     // N x ld
+  DevBuf<float> rcenter;        // per row: last iteration's row-dot, the centre dq is stored relative to
 };
 
 // Optional per-kernel CUDA-event timing (tgb200_profile_step).
@@ -232,7 +239,9 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   auto A = [&](int s) { if (st == TGB200_OK) st = s; };
   A(h->M.alloc(nv)); A(h->m.alloc(nv)); A(h->v.alloc(nv));
   if (h->bf16) {
-    h->z_parts = tc_bwd_col_parts(h->V);
+    const char* bw = getenv("TGB200_BWD");          // "fused": the round-1 three-contraction pipeline (A/B measurements)
+    h->staged = !(bw && strcmp(bw, "fused") == 0);
+    h->z_parts = h->staged ? 1 : tc_bwd_col_parts(h->V);
     A(h->Sxs.alloc((size_t)h->N * h->Ke)); A(h->lse0.alloc(h->N)); A(h->lse1.alloc(h->N)); A(h->inv_zt.alloc(h->N));
     A(h->zpart.alloc((size_t)h->z_parts * h->N));
     if (cfg->lambda_r != 0.f) A(h->pxpart.alloc((size_t)h->z_parts * h->N));
@@ -240,6 +249,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     h->lseA = h->lse0.p; h->lseT = h->lse1.p;
   }
   if (h->bf16) { A(h->rowc.alloc(h->N)); A(h->Pb.alloc(nv)); A(h->Sxb.alloc((size_t)h->N * h->Ke)); A(h->dYb.alloc(vk)); }
+  if (h->staged) { A(h->dq.alloc(nv, false)); A(h->rcenter.alloc(h->N)); }
   else if (h->x3) { A(h->Pb.alloc(3 * nv)); A(h->Sxb.alloc((size_t)3 * h->N * h->Ke)); A(h->dYb.alloc(3 * vk)); }
   else A(h->Pf.alloc(nv));
   A(h->Sx.alloc((size_t)h->N * h->Ke));
@@ -266,6 +276,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   h->rd_splits = h->tcm ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
   if (h->x3) { const int c = tc_splits_for_chain(h->V, 2048); if (c > h->rd_splits) h->rd_splits = c; }
   h->r_parts = (int)ceil_div(h->Ke, h->tcm ? TC_RDOT_BN : SG_BN) * h->rd_splits;
+  if (h->staged) h->r_parts = (int)ceil_div(h->V, TC_BWD_BN) * 2;      // TcEpiDpStore: one partial per (voxel tile, column half)
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
   // voxel rows per CTA of the loss reductions: enough CTAs for small V, bounded partial arrays for large V
@@ -454,6 +465,7 @@ extern "C" int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indp
 static int reset_optimizer(tgb200_mapper* h, cudaStream_t s) {
   CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
   CK(cudaMemsetAsync(h->v.p, 0, h->v.n * sizeof(float), s));
+  if (h->staged) CK(cudaMemsetAsync(h->rcenter.p, 0, h->rcenter.n * sizeof(float), s));
   h->step = 0;
   h->hist_len = 0;
   h->in_step = false;
@@ -503,11 +515,16 @@ extern "C" int tgb200_get_filter(tgb200_mapper* h, float* F_out, float* f_out, v
 }
 
 extern "C" int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void* stream) {
+  return tgb200_init_mapping_normal_rows(h, seed, 0, stream);
+}
+
+extern "C" int tgb200_init_mapping_normal_rows(tgb200_mapper* h, uint64_t seed, int64_t first_row, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (first_row < 0) return fail(TGB200_ERR_INVALID, "first_row < 0");
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
   const long long nq = (long long)h->N * (h->ld / 4);
-  k_init_normal<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->M.p, h->N, h->V, h->ld, seed);
+  k_init_normal<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->M.p, h->N, h->V, h->ld, seed, (long long)first_row);
   LAUNCH_CHECK("init_normal");
   CKS(reset_optimizer(h, s));
   h->have_mapping = true;
@@ -593,9 +610,12 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
   const size_t vk = (size_t)h->V * h->Ke;
   float* out = h->fwd_splits > 1 ? h->Ypart.p : h->Y.p;
   if (h->tcm) {
-    const __nv_bfloat16* sB = h->bf16 ? h->Sxs.p : h->Sxb.p;
-    CKS(tc_forward(h->tc, h->Pb.p, (size_t)h->N * h->ld, sB, (size_t)h->N * h->Ke, h->n_pairs, out, h->N, h->V, h->Ke, h->ld,
-                   h->fwd_splits, s, g_err, sizeof(g_err)));
+    if (!h->plan_fwd.ready) {
+      const __nv_bfloat16* sB = h->bf16 ? h->Sxs.p : h->Sxb.p;
+      CKS(tc_forward_plan(h->tc, h->plan_fwd, h->Pb.p, (size_t)h->N * h->ld, sB, (size_t)h->N * h->Ke, h->x3 ? 3 : 1, h->N, h->V, h->Ke,
+                          h->ld, g_err, sizeof(g_err)));
+    }
+    CKS(tc_forward_launch(h->tc, h->plan_fwd, h->n_pairs, out, h->N, h->V, h->Ke, h->fwd_splits, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_fwd");
   } else {
     GemmArgs g;
@@ -718,6 +738,36 @@ static AdamScalars adam_scalars(const tgb200_config& c, int64_t t, float lr) {
   return a;
 }
 
+static int filter_update(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a) {
+  const AdamScalarsF af{a.one_minus_beta1, a.beta2, a.one_minus_beta2, a.step_size, a.bc2_sqrt, a.eps};
+  k_filter_update<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->N, h->rdot.p, h->fsig.p, h->fscal.p, h->cfg.lambda_count,
+                                                                 h->cfg.lambda_f_reg, af, h->Fl.p, h->mF.p, h->vF.p);
+  LAUNCH_CHECK("filter_update");
+  return TGB200_OK;
+}
+
+// Staged backward (bf16 mode): dq = bf16(S_ext dY_ext^T - centre) + row-dot partials from the store-only contraction,
+// then one streaming pass does softmax-Jacobian + Adam + the next forward's P.  (mapping_optimizer.py:395-396)
+static int backward_staged(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a) {
+  if (!h->plan_dp.ready) CKS(tc_dpstore_plan(h->tc, h->plan_dp, h->Sxb.p, h->dYb.p, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+  TcEpiDpStore epi{h->dq.p, h->Pb.p, h->ld, h->rcenter.p, h->rpart.p, h->N};
+  CKS(tc_dpstore_launch(h->tc, h->plan_dp, epi, 0, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+  mark(h, s, "tc_gemm_bwd_dp");
+  k_rowdot_finalize_staged<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, 0, h->N, h->lseT, h->inv_zt.p,
+                                                                         h->stats.p, h->rcenter.p, h->rdot.p, h->rowc.p);
+  LAUNCH_CHECK("rowdot_finalize");
+  if (h->constrained) CKS(filter_update(h, s, a));
+  AdamRowsArgs ar{h->M.p, h->m.p, h->v.p, h->dq.p, h->Pb.p, reinterpret_cast<const RowConst*>(h->rowc.p),
+                  h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p, h->ld, h->V, 0, h->N,
+                  h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+  if (adam_rows_launch(ar, s)) return fail(TGB200_ERR_CUDA, "launch adam_rows: %s", cudaGetErrorString(cudaGetLastError()));
+  mark(h, s, "adam_rows");
+  // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
+  float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
+  h->p_state = 2;
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   cudaStream_t s = (cudaStream_t)stream;
@@ -731,9 +781,14 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
 
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
   const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
+  if (h->staged) {
+    CKS(backward_staged(h, s, a));
+  } else {
   if (h->tcm) {
-    CKS(tc_rowdot(h->tc, h->Pb.p, nvp, h->dYb.p, vkp, h->n_pairs, h->Sxb.p, h->x3 ? s_act(h) : nullptr, h->rpart.p, h->N, h->V,
-                  h->Ke, h->ld, h->rd_splits, s, g_err, sizeof(g_err)));
+    if (!h->plan_rd.ready)
+      CKS(tc_rowdot_plan(h->tc, h->plan_rd, h->Pb.p, nvp, h->dYb.p, vkp, h->x3 ? 3 : 1, h->N, h->V, h->Ke, h->ld, g_err, sizeof(g_err)));
+    CKS(tc_rowdot_launch(h->tc, h->plan_rd, h->n_pairs, h->Sxb.p, h->x3 ? s_act(h) : nullptr, h->rpart.p, h->N, h->V, h->Ke, h->rd_splits,
+                         s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_rowdot");
   } else {
     GemmArgs g;
@@ -751,25 +806,25 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p, h->stats.p, nullptr);
   }
   LAUNCH_CHECK("rowdot_finalize");
-  if (h->constrained) {
-    const AdamScalarsF af{a.one_minus_beta1, a.beta2, a.one_minus_beta2, a.step_size, a.bc2_sqrt, a.eps};
-    k_filter_update<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->N, h->rdot.p, h->fsig.p, h->fscal.p, h->cfg.lambda_count,
-                                                                   h->cfg.lambda_f_reg, af, h->Fl.p, h->mF.p, h->vF.p);
-    LAUNCH_CHECK("filter_update");
-  }
-  if (h->bf16) {
-    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, reinterpret_cast<const RowConst*>(h->rowc.p), h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
-                  nullptr, nullptr, h->Pb.p, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p};
-    CKS(tc_backward(h->tc, h->Sxb.p, nkp, h->dYb.p, vkp, 1, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
-    mark(h, s, "tc_gemm_bwd_adam");
-    // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
-    float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
-    h->p_state = 2;
-  } else if (h->x3) {
+  if (h->constrained) CKS(filter_update(h, s, a));
+  if (h->tcm) {
     TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, nullptr, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
-                  h->stats.p, h->rdot.p, nullptr, nullptr, nullptr, nullptr, nullptr};
-    CKS(tc_backward(h->tc, h->Sxb.p, nkp, h->dYb.p, vkp, 6, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (h->bf16) {
+      ta.rowc = reinterpret_cast<const RowConst*>(h->rowc.p);
+      ta.Pt = h->Pb.p; ta.zpart = h->zpart.p; ta.pxpart = h->pxpart.p; ta.l1part = h->l1part.p; ta.l2part = h->l2part.p;
+    } else {
+      ta.stats = h->stats.p; ta.rdot = h->rdot.p;
+    }
+    if (!h->plan_bwd.ready)
+      CKS(tc_backward_plan(h->tc, h->plan_bwd, h->Sxb.p, nkp, h->dYb.p, vkp, h->x3 ? 3 : 1, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    CKS(tc_backward_launch(h->tc, h->plan_bwd, h->n_pairs, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_bwd_adam");
+    if (h->bf16) {
+      // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
+      float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
+      h->p_state = 2;
+    }
   } else {
     GemmArgs g;
     g.A = s_act(h); g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
@@ -778,6 +833,7 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     dim3 grid((unsigned)ceil_div(h->V, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
     k_gemm_simt<true, true, EpiAdam><<<grid, SG_THREADS, 0, s>>>(g, epi);
     LAUNCH_CHECK("simt_gemm_bwd_adam");
+  }
   }
   h->step++;
   h->hist_len++;
@@ -849,7 +905,10 @@ extern "C" int tgb200_set_state(tgb200_mapper* h, const float* M, const float* m
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
   const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
-  if (M) { CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; h->p_state = 0; }
+  if (M) {
+    CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; h->p_state = 0;
+    if (h->staged) CK(cudaMemsetAsync(h->rcenter.p, 0, h->rcenter.n * sizeof(float), s));
+  }
   if (m) CK(cudaMemcpy2DAsync(h->m.p, pitch, m, w, w, h->N, cudaMemcpyDefault, s));
   if (v) CK(cudaMemcpy2DAsync(h->v.p, pitch, v, w, w, h->N, cudaMemcpyDefault, s));
   h->step = step;

@@ -67,8 +67,8 @@ class Engine:
     def set_mapping(self, M0, stream=None):
         _lib.check(self._lib.tgb200_set_mapping(self._h, _lib.ptr(M0), self._s(stream)))
 
-    def init_mapping_normal(self, seed, stream=None):
-        _lib.check(self._lib.tgb200_init_mapping_normal(self._h, seed, self._s(stream)))
+    def init_mapping_normal(self, seed, stream=None, first_row=0):
+        _lib.check(self._lib.tgb200_init_mapping_normal_rows(self._h, seed, first_row, self._s(stream)))
 
     def run(self, n_steps, lr=0.1, stream=None):
         _lib.check(self._lib.tgb200_run(self._h, n_steps, lr, self._s(stream)))
@@ -106,6 +106,20 @@ class Engine:
         n_cols = int(X.shape[1])
         _lib.check(self._lib.tgb200_project(self._h, _lib.ptr(X), n_cols, _lib.ptr(out), self._s(stream)))
         return out
+
+    def get_state(self, M=None, m=None, v=None, stream=None):
+        """Copy M / m / v (n_cells x n_voxels f32, host or device buffers; None skips) out of the handle; returns the step count."""
+        step = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_get_state(self._h, _lib.ptr(M), _lib.ptr(m), _lib.ptr(v), ctypes.byref(step), self._s(stream)))
+        return step.value
+
+    def debug(self, name):
+        """Internal device buffer by name (tgb200_debug_buffer) as a host array."""
+        n = ctypes.c_int64()
+        _lib.check(self._lib.tgb200_debug_buffer(self._h, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.empty(max(n.value, 4), dtype=np.float32)
+        _lib.check(self._lib.tgb200_debug_buffer(self._h, name.encode(), _lib.ptr(out), out.size, ctypes.byref(n)))
+        return out[:n.value]
 
     def kernel_launches(self):
         n = ctypes.c_int64()
