@@ -7,7 +7,8 @@ bench.py -- map_cells_to_space iterations/sec on B200 (BASELINE.json metric).
 
 A "step" is one optimizer iteration (loss, backward, Adam) of the hot path on synthetic
 expression-like inputs.  N>1: launched by torchrun, one rank per GPU, the
-cells axis sharded (strong scaling: the total problem is fixed), one NCCL all-reduce per step.
+cells axis sharded (strong scaling: the total problem is fixed), one NCCL all-reduce per step issued by the library itself
+(tgb200_comm_init_rank + tgb200_run).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -234,8 +235,7 @@ def timed_steps(one_step, barrier, steps, flush_buf):
     if flush_buf is None:
         barrier()
         e0.record()
-        for _ in range(steps):
-            one_step()
+        one_step(steps)                   # one tgb200_run(K): what Mapper.train(K) issues
         e1.record()
         barrier()
         return e0.elapsed_time(e1) / 1e3
@@ -244,7 +244,7 @@ def timed_steps(one_step, barrier, steps, flush_buf):
         flush_buf.zero_()
         barrier()
         e0.record()
-        one_step()
+        one_step(1)
         e1.record()
         barrier()
         elapsed += e0.elapsed_time(e1) / 1e3
@@ -414,23 +414,24 @@ def main():
     SEED = 1234
     eng.init_mapping_normal(SEED, first_row=r0)      # device Philox keyed by the global cell index: same M0 at every N
     stream = torch.cuda.current_stream().cuda_stream
-    xbuf = eng.exchange_tensor() if world > 1 else None
+    if world > 1:
+        # the handle's own NCCL communicator (tgb200_comm_init_rank): the per-iteration exchange runs inside tgb200_run;
+        # torch.distributed only carries the 128-byte id
+        def bcast(uid):
+            t = torch.from_numpy(uid).cuda()
+            dist.broadcast(t, src=0)
+            return t.cpu().numpy()
+        eng.comm_init(rank, world, bcast)
 
-    def one_step():
-        if world == 1:
-            eng.run(1, 0.1, stream)
-        else:
-            eng.step_begin(stream)
-            dist.all_reduce(xbuf)
-            eng.step_end(0.1, stream)
+    def one_step(n=1):
+        eng.run(n, 0.1, stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        one_step()
+    one_step(a.warmup)
     barrier()
     state_bytes = 3.0 * 4 * N * V / world
     flush = state_bytes < 2 * L2_BYTES
@@ -467,7 +468,10 @@ def main():
     prof = {}
     for _ in range(3):
         if world == 1:
+            per_step = {}                        # a kernel launched once per cell chunk: its launches of one step add up
             for name, ms in eng.profile_step(0.1, stream):
+                per_step[name] = per_step.get(name, 0.0) + ms
+            for name, ms in per_step.items():
                 prof.setdefault(name, []).append(ms)
         else:
             break
@@ -548,6 +552,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         mp = Mapper(**kw)
+        torch.cuda.synchronize()
+        t_ctor = time.perf_counter() - t0
         out, hist_e = mp.train(a.steps, learning_rate=0.1, print_each=None)
         barrier()
         dt = time.perf_counter() - t0
@@ -560,7 +566,8 @@ def main():
         e2e = {"value": a.steps / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d / a.steps,
                "d2h_bytes_per_step": d2h / a.steps,
                "what": f"Mapper(S,G,d,M0 in pinned host memory).train({a.steps}): upload + {a.steps} iterations + softmax(M) download; "
-                       f"total {dt:.2f} s per rank (copies are per call, not per iteration).  The initial mapping is passed in: the "
+                       f"total {dt:.2f} s per rank ({t_ctor:.2f} s create + upload, {dt - t_ctor:.2f} s iterations + download; copies are per "
+                       f"call, not per iteration).  The initial mapping is passed in: the "
                        f"reference API's default host-side float64 draw of M0 (mapping_optimizer.py:150) is outside this region "
                        f"(reference_gpu.init_s shows what it costs)"}
         del mp, out, M0, Sp
@@ -583,6 +590,10 @@ def main():
                 "data": "synthetic", "config": dict(config, precision=a.precision,
                                                     l2="L2 flushed between timed iterations" if flush else "state exceeds L2 (no flush)"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "collective": ({"name": "ncclAllReduce(sum, f32) of the exchange buffer [Y_ext (voxels x Ke) | 8 row-scalar partials], in place",
+                                "bytes_per_step_per_rank": (V * (-(-(K + 2 + T) // 64) * 64) + 8) * 4, "per_step": 1,
+                                "issued_by": "tgb200_run on the handle's own stream (communicator from tgb200_comm_init_rank)"}
+                               if world > 1 else None),
                 "parity": parity, "reference_gpu": refgpu,
                 "vs_reference_gpu": (value / refgpu["value"]) if refgpu else None, "bf16x3": x3}
         print(json.dumps(line))

@@ -140,6 +140,10 @@ TGB200_API int tgb200_init_mapping_normal(tgb200_mapper* h, uint64_t seed, void*
  * cell does not depend on how the cells are sharded over ranks (tgb200_init_mapping_normal == first_row 0). */
 TGB200_API int tgb200_init_mapping_normal_rows(tgb200_mapper* h, uint64_t seed, int64_t first_row, void* stream);
 
+/* A fresh optimizer on the current mapping: what every Mapper.train call does when it builds torch.optim.Adam([M])
+ * anew (:373, :607) -- zero moments, bias correction restarts at t = 1.  M, F, the history and its length are kept. */
+TGB200_API int tgb200_reset_adam(tgb200_mapper* h, void* stream);
+
 /* Constrained mode: initial filter logits F0 (n_cells, host or device; the reference draws them at :490).
  * Resets the filter's Adam state. */
 TGB200_API int tgb200_set_filter(tgb200_mapper* h, const float* F0, void* stream);
@@ -154,10 +158,24 @@ TGB200_API int tgb200_run(tgb200_mapper* h, int32_t n_steps, float learning_rate
 
 /* Cell-sharded operation (one handle per rank): step_begin computes this rank's partial
  * sums; the caller all-reduces (sum) the exchange buffer across ranks (NCCL); step_end
- * finishes the iteration.  tgb200_run == step_begin + step_end when not sharded. */
+ * finishes the iteration.  tgb200_run == step_begin + step_end when not sharded, and step_begin + NCCL all-reduce +
+ * step_end on a sharded handle that has a communicator (below). */
 TGB200_API int tgb200_step_begin(tgb200_mapper* h, void* stream);
 TGB200_API int tgb200_exchange_buffer(tgb200_mapper* h, float** device_ptr, int64_t* n_floats);
 TGB200_API int tgb200_step_end(tgb200_mapper* h, float learning_rate, void* stream);
+
+/* Cell-sharded operation without the caller in the loop: give the handle the NCCL communicator of the ranks that share
+ * the voxels (one rank per GPU, each holding a contiguous block of cells; n_cells_global = the total) and tgb200_run
+ * issues the per-iteration exchange itself, on its own streams, overlapped with the update of the previous iteration.
+ * The reference has no multi-device path at all (one torch.device, mapping_utils.py:310); this replaces a user-level
+ * loop around Mapper.train.  NCCL is bound at run time (libnccl.so.2 via dlopen: the instance already loaded in the
+ * process, e.g. PyTorch's, else the system one).
+ *   tgb200_comm_unique_id   rank 0: 128 opaque bytes (ncclGetUniqueId) to hand to every rank by any means
+ *   tgb200_comm_init_rank   every rank: ncclCommInitRank on the handle's device; the handle owns the communicator
+ *   tgb200_set_comm         alternatively borrow an existing ncclComm_t (NULL detaches); the caller keeps ownership */
+TGB200_API int tgb200_comm_unique_id(void* id_out_128_bytes, int64_t capacity);
+TGB200_API int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id_128_bytes, int32_t rank, int32_t world);
+TGB200_API int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, int32_t world);
 
 /* ---- outputs ----------------------------------------------------------------------- */
 
@@ -194,6 +212,12 @@ TGB200_API int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, doub
  * "dY" (V x Ke), "rdot" (n_cells), "Sx" (n_cells x Ke), "shape" (Ke, ld, fwd_splits, r_parts).
  * out_host may be NULL to query the size (*n). */
 TGB200_API int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* out_host, int64_t cap, int64_t* n);
+
+/* Diagnostics: enable != 0 starts recording a CUDA event after every launch on the stream it went to; enable == 0 stops
+ * and returns, per launch, its name, stream (0 caller, 1 the handle's contraction stream, 2 its update stream) and
+ * completion time in ms relative to the first one -- the only way to see the two-stream pipeline without a tracer. */
+TGB200_API int tgb200_debug_timeline(tgb200_mapper* h, int32_t enable, const char** names, int32_t* streams, float* end_ms,
+                                     int32_t cap, int32_t* n);
 
 /* Host-binding helpers for the result of Mapper.train (softmax(M).cpu().numpy(), mapping_optimizer.py:406-408): fault in and
  * page-lock a caller-owned host buffer so that tgb200_get_mapping's device->host copy runs as one DMA at link speed.  Meant to

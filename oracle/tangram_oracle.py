@@ -289,6 +289,10 @@ class OracleMapper:
         val_keys = ["val_total_loss", "val_gene_sim", "val_sp_sparsity_weighted_sim", "val_entropy"]
         history = {k: [] for k in keys + val_keys}
         self.terms_history = []
+        # :373 -- `torch.optim.Adam([self.M], lr)` is built inside train(): every call starts from zero moments, t = 0
+        self.m = torch.zeros_like(self.M)
+        self.v = torch.zeros_like(self.M)
+        self.t = 0
         for t in range(num_epochs):
             terms, dM = self.loss_and_grad()
             self.terms_history.append(terms)

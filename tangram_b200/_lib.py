@@ -50,12 +50,16 @@ SIGNATURES = {
     "tgb200_set_mapping": (ctypes.c_int, [_P, _P, _P]),
     "tgb200_init_mapping_normal": (ctypes.c_int, [_P, ctypes.c_uint64, _P]),
     "tgb200_init_mapping_normal_rows": (ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int64, _P]),
+    "tgb200_reset_adam": (ctypes.c_int, [_P, _P]),
     "tgb200_set_filter": (ctypes.c_int, [_P, _P, _P]),
     "tgb200_get_filter": (ctypes.c_int, [_P, _P, _P, _P]),
     "tgb200_run": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_float, _P]),
     "tgb200_step_begin": (ctypes.c_int, [_P, _P]),
     "tgb200_exchange_buffer": (ctypes.c_int, [_P, ctypes.POINTER(_P), _I64]),
     "tgb200_step_end": (ctypes.c_int, [_P, ctypes.c_float, _P]),
+    "tgb200_comm_unique_id": (ctypes.c_int, [_P, ctypes.c_int64]),
+    "tgb200_comm_init_rank": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
+    "tgb200_set_comm": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "tgb200_history_len": (ctypes.c_int, [_P, _I64]),
     "tgb200_get_history": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     "tgb200_get_mapping": (ctypes.c_int, [_P, _P, _P]),
@@ -67,6 +71,7 @@ SIGNATURES = {
     "tgb200_profile_step": (ctypes.c_int, [_P, ctypes.c_float, _P, ctypes.POINTER(ctypes.c_char_p), _F,
                                            ctypes.c_int32, _I32]),
     "tgb200_algorithmic_cost": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "tgb200_debug_timeline": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), _I32, _F, ctypes.c_int32, _I32]),
     "tgb200_debug_buffer": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_int64, _I64]),
     "tgb200_host_pin": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     "tgb200_host_unpin": (ctypes.c_int, [_P]),

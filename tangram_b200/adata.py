@@ -55,6 +55,16 @@ class MiniAnnData:
                 out.append(g)
         self.var.index = out
 
+    def _inplace_subset_var(self, keep):
+        """In-place column subset (the method scanpy's filter_genes calls on a real AnnData): X, var and the per-gene
+        arrays shrink together."""
+        c = self._rows(keep, self.var.index)
+        if self.X is not None:
+            self.X = self.X[:, c] if hasattr(self.X, "tocsr") else np.asarray(self.X)[:, c]
+        self.var = self.var.iloc[c].copy()
+        if getattr(self, "varm", None):
+            self.varm = {k: np.asarray(v)[c] for k, v in self.varm.items()}
+
     def _rows(self, key, index):
         if isinstance(key, slice):
             return np.arange(len(index))[key]

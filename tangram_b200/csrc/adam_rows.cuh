@@ -42,8 +42,11 @@ __device__ __forceinline__ uint4 ldg128_stream(const void* src) {
 struct AdamRowsLoad { float x[8], m[8], v[8]; uint4 d; };
 
 // PLAIN: default loss (no entropy / L1 / L2) -> packed f32x2 arithmetic, 4 MUFU per element.
+#ifndef TGB_ADAM_MAXNREG
+#define TGB_ADAM_MAXNREG 96     // 2 CTAs of this kernel + one contraction CTA (192 threads) per SM: 2 x 24.5K + 13.8K registers
+#endif
 template <bool PLAIN>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(TGB_ADAM_MAXNREG)
 k_adam_rows(const AdamRowsArgs p) {
   const int lane = threadIdx.x & 31;
   const int row = p.row0 + blockIdx.x * 8 + (threadIdx.x >> 5);

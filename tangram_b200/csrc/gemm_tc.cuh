@@ -347,28 +347,30 @@ struct TcEpiRowDot {
 struct TcEpiDpStore {
   __nv_bfloat16* dq; const __nv_bfloat16* Pt; int ld;     // both [rows][ld]
   const float* center;                                    // c_i (per row)
-  float* rpart;                                           // [tiles_n * 2][M]
+  float* rpart;                                           // [tiles_n * (NW / 4)][M]
   int M;
   static constexpr int kStagingBytes = 0;
+  // NW = 4: one warp per TMEM lane quarter takes all BN columns; NW = 8: two warps, BN / 2 columns each.  Four warps keep
+  // the CTA small (192 threads) so that two CTAs of the streaming Adam kernel fit next to it on the SM.
   template <int BN, int NW>
   __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx&) const {
-    static_assert(NW == 8, "two warps per TMEM lane quarter");
-    const int row = t.m0 + q * 32 + lane, col = t.n0 + (ew >> 2) * (BN / 2);
+    static_assert(NW == 4 || NW == 8, "one or two warps per TMEM lane quarter");
+    constexpr int W = BN / (NW / 4);
+    const int row = t.m0 + q * 32 + lane, col = t.n0 + (ew >> 2) * W;
     if (row < M) {
       const __nv_bfloat16* src = Pt + (size_t)row * ld + col;
 #pragma unroll
-      for (int b = 0; b < BN / 2; b += 64)      // 128-byte lines of this thread's row segment
+      for (int b = 0; b < W; b += 64)           // 128-byte lines of this thread's row segment
         if (col + b < ld) prefetch_l2(src + b);
     }
   }
   __device__ __forceinline__ void finish(int, int, int) const {}
   template <int BN, int NW>
   __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx&) const {
-    static_assert(NW == 8, "two warps per TMEM lane quarter");
-    constexpr int NCH = BN / 2 / 16;
+    constexpr int PARTS = NW / 4, W = BN / PARTS, NCH = W / 16;
     const int part = ew >> 2;
     const int row = t.m0 + q * 32 + lane;
-    const int cbase = t.n0 + part * (BN / 2);
+    const int cbase = t.n0 + part * W;
     const bool live = row < M;
     const float c = live ? center[row] : 0.f;
     const __nv_bfloat16* prow = Pt + (size_t)row * ld;
@@ -395,7 +397,7 @@ struct TcEpiDpStore {
         stg256(drow + col0, w);
       }
     }
-    if (live) rpart[((size_t)t.tile_n * 2 + part) * M + row] = racc;
+    if (live) rpart[((size_t)t.tile_n * PARTS + part) * M + row] = racc;
   }
 };
 
@@ -732,7 +734,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
           const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
           const __grid_constant__ CUtensorMap map_e2,
           int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, int group_m, uint64_t policy_a,
-          uint64_t policy_b, int tm_off, const Epi epi) {
+          uint64_t policy_b, int tm_off, int k_off, const Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
   using TileB = OperandTile<B_KMAJOR, BN>;
   constexpr int kStageBytes = TileA::kBytes + TileB::kBytes;
@@ -779,7 +781,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
         int tm_i, tn_i;
         tile_mn(w - z * tiles_n * tiles_m, tiles_m, tiles_n, group_m, tm_i, tn_i);
         const int n0 = tn_i * BN, m0 = (tm_off + tm_i) * TC_BM;
-        const int k_begin = z * k_per_split;
+        const int k_begin = k_off + z * k_per_split;
         const int k_end = min(k_total, k_begin + k_per_split);
         const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
         for (int pr = 6 - n_pairs; pr < 6; ++pr) {
@@ -806,7 +808,7 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
       int it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         const int z = w / (tiles_n * tiles_m);
-        const int k_begin = z * k_per_split;
+        const int k_begin = k_off + z * k_per_split;
         const int k_end = min(k_total, k_begin + k_per_split);
         const int num_kb = (k_end - k_begin + TC_BK - 1) / TC_BK;
         const int b = it & 1;
@@ -1181,7 +1183,11 @@ constexpr int TC_PAIR_STAGES = TGB_PAIR_STAGES, TC_PAIR_MIN_ROWS = 2048;
 #ifndef TGB_DP_STAGES
 #define TGB_DP_STAGES 6
 #endif
-constexpr int TC_DP_STAGES = TGB_DP_STAGES, TC_DP_SINGLE_STAGES = 4;
+#ifndef TGB_DP_EPI_WARPS
+#define TGB_DP_EPI_WARPS 4
+#endif
+constexpr int TC_DP_STAGES = TGB_DP_STAGES, TC_DP_SINGLE_STAGES = 4, TC_DP_EPI_WARPS = TGB_DP_EPI_WARPS;
+static inline int tc_dp_row_parts(int V) { return (int)ceil_div(V, TC_BWD_BN) * (TC_DP_EPI_WARPS / 4); }
 // Row tiles per scheduling group of the backward kernel (tile_mn).  Measured at 100k x 10k x 2k, ms per launch:
 // 1: 5.75   4: 5.84   8: 5.86   16: 5.89   37: 7.03 -- many CTAs pulling the same B tile at once hot-spot L2 slices.
 #ifndef TGB_BWD_GROUP
@@ -1256,7 +1262,20 @@ static inline int tc_forward_launch(TcContext& tc, const TcPlan& pl, int n_pairs
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
   kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], N, tc_kps(N, splits), tm, tn,
-                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, epi);
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, 0, epi);
+  return tc_check_launch("tc_gemm_fwd", err, n);
+}
+// cells [row0, row1) only (row0 a multiple of 64): partial sum into `out` -- the host pipelines cell chunks behind the
+// streaming Adam kernel and k_loss_reduce adds the planes
+static inline int tc_forward_launch_rows(TcContext& tc, const TcPlan& pl, float* out, int row0, int row1, int V, int Ke, cudaStream_t s,
+                                         char* err, size_t n) {
+  auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
+  const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
+  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
+  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
+  const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], row1, (int)round_up(row1 - row0, TC_BK), tm, tn,
+                                                                1, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, row0, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
 // one-shot variant for temporary operands (tgb200_project)
@@ -1284,7 +1303,7 @@ static inline int tc_rowdot_launch(TcContext& tc, const TcPlan& pl, int n_pairs,
   TcEpiRowDot epi{Sxb, Ke, rpart, N, Sxf};
   const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
   kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], V, tc_kps(V, splits), tm, tn,
-                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, 0, epi);
+                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, 0, 0, epi);
   return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
@@ -1359,7 +1378,7 @@ static inline int tc_backward_launch(TcContext& tc, const TcPlan& pl, int n_pair
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   const int tm = (int)ceil_div(N, TC_BM);
   kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(pl.a, pl.b, n_pairs, pl.e[0], pl.e[1], pl.e[2], Ke, Ke, tm, tn, 1,
-                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, 0, epi);
+                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, 0, 0, epi);
   return tc_check_launch("tc_gemm_bwd_adam", err, n);
 }
 
@@ -1371,10 +1390,10 @@ static inline int tc_dpstore_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16
   pl.pair = false;
 #if TGB_BWD_PAIR
   if (N >= TC_PAIR_MIN_ROWS) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, 8, TcEpiDpStore>;
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
     const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
     if (tc_set_smem(tc, pk, psmem, err, n)) return -2;
-    if (tc.dp_clusters < 0) tc.dp_clusters = tc_pair_clusters(tc, pk, 64 + 32 * 8, psmem, s);
+    if (tc.dp_clusters < 0) tc.dp_clusters = tc_pair_clusters(tc, pk, 64 + 32 * TC_DP_EPI_WARPS, psmem, s);
     pl.pair = tc.dp_clusters > 0;
   }
 #endif
@@ -1386,22 +1405,22 @@ static inline int tc_dpstore_launch(TcContext& tc, const TcPlan& pl, const TcEpi
                                     cudaStream_t s, char* err, size_t n) {
   const int tn = (int)ceil_div(V, TC_BWD_BN);
   if (pl.pair) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, 8, TcEpiDpStore>;
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
     const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
     const int tm0 = row0 / (2 * TC_BM), tmp = (int)ceil_div(row1, 2 * TC_BM) - tm0;
     const long long pair_tiles = (long long)tmp * tn;
     const unsigned clusters = (unsigned)(pair_tiles < tc.dp_clusters ? pair_tiles : tc.dp_clusters);
-    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * 8, psmem, s, pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, tmp, tn, 1,
+    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * TC_DP_EPI_WARPS, psmem, s, pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, tmp, tn, 1,
                                    (uint64_t)kPolicyEvictNormal, (uint64_t)kPolicyEvictLast, tm0, epi);
     if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_dp (pair): %s", cudaGetErrorString(e)); return -2; }
     return tc_check_launch("tc_gemm_bwd_dp", err, n);
   }
-  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_DP_SINGLE_STAGES, 8, TcEpiDpStore>;
+  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_DP_SINGLE_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
   const int smem = TC_DP_SINGLE_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   const int tm0 = row0 / TC_BM, tm = (int)ceil_div(row1, TC_BM) - tm0;
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 8, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, Ke, tm, tn, 1, 1,
-                                                                 kPolicyEvictNormal, kPolicyEvictLast, tm0, epi);
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_DP_EPI_WARPS, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, Ke, tm, tn, 1, 1,
+                                                                                kPolicyEvictNormal, kPolicyEvictLast, tm0, 0, epi);
   return tc_check_launch("tc_gemm_bwd_dp", err, n);
 }
 

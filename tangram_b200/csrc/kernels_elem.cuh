@@ -664,9 +664,9 @@ __global__ void k_init_normal(float* __restrict__ M, int rows, int V, int ld, un
 __global__ void k_row_norm(int n_rows, int fresh, const float* __restrict__ zpart, const float* __restrict__ pxpart,
                            const float* __restrict__ l1part, const float* __restrict__ l2part, int nparts,
                            const float* __restrict__ lseA, float* __restrict__ lseT, float* __restrict__ inv_zt,
-                           RowStat* __restrict__ stats, float* __restrict__ rowaux) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows) return;
+                           RowStat* __restrict__ stats, float* __restrict__ rowaux, int row0, int row1) {
+  const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row0, row1) of n_rows
+  if (i >= row1) return;
   if (fresh) {
     const RowStat st = stats[i];
     lseT[i] = st.mx + st.log_z;
@@ -690,11 +690,11 @@ __global__ void k_row_norm(int n_rows, int fresh, const float* __restrict__ zpar
   if (rowaux && l1part) { rowaux[2 * i] = a; rowaux[2 * i + 1] = b; }
 }
 // Sxs[i][:] = bf16(Sx[i][:] * inv_zt[i]): the forward B operand carries the row normalisation
-__global__ void k_scale_rows_bf16(const float* __restrict__ Sx, const float* __restrict__ inv_zt, int n_rows, int ld,
+__global__ void k_scale_rows_bf16(const float* __restrict__ Sx, const float* __restrict__ inv_zt, int row0, int row1, int ld,
                                   __nv_bfloat16* __restrict__ out) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 each
   const int nvec = ld >> 2;
-  if (q >= (long long)n_rows * nvec) return;
+  const long long q = (long long)row0 * nvec + (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 each, rows [row0, row1)
+  if (q >= (long long)row1 * nvec) return;
   const int r = (int)(q / nvec);
   const float s = inv_zt[r];
   const float4 v = reinterpret_cast<const float4*>(Sx)[q];

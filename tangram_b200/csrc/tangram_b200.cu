@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "adam_rows.cuh"
+#include "nccl_dl.h"
 
 using namespace tgb;
 
@@ -129,6 +130,35 @@ struct tgb200_mapper {
   bool staged = false;
   DevBuf<__nv_bfloat16> dq;     // N x ld
   DevBuf<float> rcenter;        // per row: last iteration's row-dot, the centre dq is stored relative to
+  // Pipelining of the staged backward over cell chunks (rows [chunk_row[c], chunk_row[c+1]), multiples of 256):
+  //   hi (high-priority stream): forward(c) ... loss ... backward contraction(c)        -- tensor-core bound
+  //   lo (low-priority stream):  row-dot finalize(c), streaming Adam(c)                 -- HBM bound
+  // Adam(c) runs under the contraction of chunk c+1 and, across the iteration boundary, under the next forward's
+  // chunks; forward(c) of the next iteration waits only for Adam(c).  The caller's stream forks into hi at the
+  // start of an API call and joins hi + lo at its end (tgb200_run joins once, after its last iteration).
+  bool pipelined = false;
+  int nchunks = 1, chunk_row[9] = {0};
+  cudaStream_t hi = nullptr, lo = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join_hi = nullptr, ev_join_lo = nullptr, ev_g[8] = {}, ev_a[8] = {};
+  bool a_valid = false;         // ev_a[] were recorded by an earlier step_end and guard the rows of the next forward
+  bool defer_join = false;      // inside tgb200_run: no fork / join between its iterations
+  bool serial = false;          // tgb200_profile_step: everything on the caller's stream, one kernel at a time
+  // diagnostics (tgb200_debug_timeline): completion time of every launch on its stream
+  bool timeline_on = false;
+  std::vector<const char*> tl_names;
+  std::vector<int> tl_streams;
+  std::vector<cudaEvent_t> tl_events;
+  // cell-sharded operation: NCCL communicator of the ranks that share the voxels (tgb200_comm_init_rank / tgb200_set_comm)
+  void* comm = nullptr;
+  bool comm_owned = false;
+  int comm_rank = 0, comm_world = 1;
+  ~tgb200_mapper() {
+    if (comm && comm_owned) { char e[64]; if (NcclApi* a = nccl_api(e, sizeof(e))) a->CommDestroy(comm); }
+    if (hi) cudaStreamDestroy(hi);
+    if (lo) cudaStreamDestroy(lo);
+    for (cudaEvent_t e : {ev_fork, ev_join_hi, ev_join_lo}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 8; ++i) { if (ev_g[i]) cudaEventDestroy(ev_g[i]); if (ev_a[i]) cudaEventDestroy(ev_a[i]); }
+  }
 };
 
 // Optional per-kernel CUDA-event timing (tgb200_profile_step).
@@ -138,6 +168,14 @@ struct KernelTimer {
 };
 static void mark(tgb200_mapper* h, cudaStream_t s, const char* name) {
   h->launches++;
+  if (h->timeline_on) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    h->tl_names.push_back(name);
+    h->tl_streams.push_back(s == h->hi ? 1 : (s == h->lo ? 2 : 0));
+    h->tl_events.push_back(e);
+  }
   if (h->timer) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -256,6 +294,28 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   A(h->G.alloc(vk));
   A(h->d.alloc(h->V)); A(h->dsrc.alloc(h->N));
   A(h->stats.alloc(h->N)); A(h->rowaux.alloc((size_t)2 * h->N)); A(h->rdot.alloc(h->N));
+  if (h->staged) {
+    // cell chunks of the pipelined backward: 4 from 32k cells up (each chunk still fills the GPU several times over)
+    int nc = (h->N >= 32768 && !h->constrained) ? 4 : 1;
+    if (const char* e = getenv("TGB200_CHUNKS")) nc = atoi(e);
+    if (nc < 1) nc = 1;
+    if (nc > 8) nc = 8;
+    if (h->constrained) nc = 1;              // the filter update couples all rows of an iteration
+    while (nc > 1 && h->N / nc < 1024) --nc;
+    h->nchunks = nc;
+    for (int c = 0; c <= nc; ++c) h->chunk_row[c] = c == nc ? h->N : (int)round_up((int64_t)c * h->N / nc, 256);
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    bool ok = cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, hi_p) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&h->lo, cudaStreamNonBlocking, lo_p) == cudaSuccess;
+    cudaEvent_t* evs[3] = {&h->ev_fork, &h->ev_join_hi, &h->ev_join_lo};
+    for (auto e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; c < 8; ++c)
+      ok = ok && cudaEventCreateWithFlags(&h->ev_g[c], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_a[c], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) A(fail(TGB200_ERR_CUDA, "stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    h->pipelined = ok;
+  }
   // forward split over cells so that the grid covers the 148 SMs (deterministic partial planes)
   {
     const int tiles = (int)(ceil_div(h->V, 128) * ceil_div(h->Ke, 128));
@@ -265,6 +325,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     if (s < 1) s = 1;
     if (h->tcm) s = tc_forward_splits(h->N, h->V, h->Ke);
     if (h->x3) { const int c = tc_splits_for_chain(h->N, 2048); if (c > s) s = c; }
+    if (h->nchunks > 1) s = h->nchunks;      // one partial plane per cell chunk (k_loss_reduce adds them)
     h->fwd_splits = s;
     if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
   }
@@ -276,7 +337,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   h->rd_splits = h->tcm ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
   if (h->x3) { const int c = tc_splits_for_chain(h->V, 2048); if (c > h->rd_splits) h->rd_splits = c; }
   h->r_parts = (int)ceil_div(h->Ke, h->tcm ? TC_RDOT_BN : SG_BN) * h->rd_splits;
-  if (h->staged) h->r_parts = (int)ceil_div(h->V, TC_BWD_BN) * 2;      // TcEpiDpStore: one partial per (voxel tile, column half)
+  if (h->staged) h->r_parts = tc_dp_row_parts(h->V);                   // TcEpiDpStore: one partial per (voxel tile, epilogue warp of a lane quarter)
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
   // voxel rows per CTA of the loss reductions: enough CTAs for small V, bounded partial arrays for large V
@@ -473,6 +534,23 @@ static int reset_optimizer(tgb200_mapper* h, cudaStream_t s) {
   return TGB200_OK;
 }
 
+// torch.optim.Adam([M], lr) is rebuilt by every Mapper.train call (mapping_optimizer.py:373, :607): fresh moments,
+// bias correction restarts at t = 1.  M (and F), the history and the resident P are kept.
+extern "C" int tgb200_reset_adam(tgb200_mapper* h, void* stream) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (h->in_step) return fail(TGB200_ERR_STATE, "reset_adam inside a step");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
+  CK(cudaMemsetAsync(h->v.p, 0, h->v.n * sizeof(float), s));
+  if (h->constrained) {
+    CK(cudaMemsetAsync(h->mF.p, 0, h->mF.n * sizeof(float), s));
+    CK(cudaMemsetAsync(h->vF.p, 0, h->vF.n * sizeof(float), s));
+  }
+  h->step = 0;
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_set_mapping(tgb200_mapper* h, const float* M0, void* stream) {
   if (!h || !M0) return fail(TGB200_ERR_INVALID, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
@@ -585,6 +663,25 @@ static int check_ready(tgb200_mapper* h) {
   return TGB200_OK;
 }
 
+// Streams of an API call: the caller's stream `s` forks into the handle's high-priority stream (which in turn feeds the
+// low-priority one through per-chunk events) and joins both at the end.
+static cudaStream_t work_stream(tgb200_mapper* h, cudaStream_t s) { return (h->pipelined && !h->serial) ? h->hi : s; }
+static cudaStream_t update_stream(tgb200_mapper* h, cudaStream_t s) { return (h->pipelined && !h->serial) ? h->lo : s; }
+static int fork_streams(tgb200_mapper* h, cudaStream_t s) {
+  if (!h->pipelined || h->serial || h->defer_join) return TGB200_OK;
+  CK(cudaEventRecord(h->ev_fork, s));
+  CK(cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
+  return TGB200_OK;
+}
+static int join_streams(tgb200_mapper* h, cudaStream_t s) {
+  if (!h->pipelined || h->serial || h->defer_join) return TGB200_OK;
+  CK(cudaEventRecord(h->ev_join_hi, h->hi));
+  CK(cudaStreamWaitEvent(s, h->ev_join_hi, 0));
+  CK(cudaEventRecord(h->ev_join_lo, h->lo));
+  CK(cudaStreamWaitEvent(s, h->ev_join_lo, 0));
+  return TGB200_OK;
+}
+
 // forward: P, row statistics, Y_ext partial sums over this handle's cells
 static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
   float* rowaux = needs_rowaux(h->cfg) ? h->rowaux.p : nullptr;
@@ -595,12 +692,25 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
       CKS(launch_softmax_rows<__nv_bfloat16>(h, s, h->Pb.p, 1, rowaux));
       h->p_state = 1;
     }
-    k_row_norm<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->N, h->p_state == 1 ? 1 : 0, h->zpart.p, h->pxpart.p, h->l1part.p,
-                                                            h->l2part.p, h->z_parts, h->lseA, h->lseT, h->inv_zt.p, h->stats.p, rowaux);
-    LAUNCH_CHECK("row_norm");
-    const long long nq = (long long)h->N * (h->Ke / 4);
-    k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, h->N, h->Ke, h->Sxs.p);
-    LAUNCH_CHECK("scale_rows");
+    if (!h->plan_fwd.ready)
+      CKS(tc_forward_plan(h->tc, h->plan_fwd, h->Pb.p, (size_t)h->N * h->ld, h->Sxs.p, (size_t)h->N * h->Ke, 1, h->N, h->V, h->Ke, h->ld,
+                          g_err, sizeof(g_err)));
+    for (int c = 0; c < h->nchunks; ++c) {
+      const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
+      // rows of this chunk: the streaming Adam kernel of the previous iteration must have written their P and row sums
+      if (h->a_valid && h->pipelined && !h->serial) CK(cudaStreamWaitEvent(s, h->ev_a[c], 0));
+      k_row_norm<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, s>>>(h->N, h->p_state == 1 ? 1 : 0, h->zpart.p, h->pxpart.p, h->l1part.p,
+                                                                 h->l2part.p, h->z_parts, h->lseA, h->lseT, h->inv_zt.p, h->stats.p, rowaux, r0, r1);
+      LAUNCH_CHECK("row_norm");
+      const long long nq = (long long)(r1 - r0) * (h->Ke / 4);
+      k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, r0, r1, h->Ke, h->Sxs.p);
+      LAUNCH_CHECK("scale_rows");
+      if (h->nchunks > 1) {
+        CKS(tc_forward_launch_rows(h->tc, h->plan_fwd, h->Ypart.p + (size_t)c * h->V * h->Ke, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
+        mark(h, s, "tc_gemm_fwd");
+      }
+    }
+    if (h->nchunks > 1) return TGB200_OK;
   } else if (h->x3) {
     // parity mode on tensor cores: exact row pass every iteration, P written as three bf16 planes
     CKS(launch_softmax_rows<float>(h, s, (float*)nullptr, want_entropy, rowaux, Split3{h->Pb.p, (size_t)h->N * h->ld}));
@@ -632,11 +742,15 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
 
 extern "C" int tgb200_step_begin(tgb200_mapper* h, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
   CKS(check_ready(h));
   if (h->in_step) return fail(TGB200_ERR_STATE, "step_begin called twice without step_end");
+  CKS(fork_streams(h, caller));
+  cudaStream_t s = work_stream(h, caller);
   if (h->constrained) {
+    // the filter logits were updated on the update stream at the end of the previous iteration
+    if (h->a_valid && h->pipelined && !h->serial) CK(cudaStreamWaitEvent(s, h->ev_a[0], 0));
     // f = sigmoid(F), S_f = f o S_ext (:507, :519) and the operand copies the contractions read
     const long long nq = (long long)h->N * (h->Ke / 4);
     k_filter_prepare<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(h->Fl.p, h->Sx.p, h->N, h->Ke, h->fsig.p, h->Sf.p);
@@ -655,6 +769,7 @@ extern "C" int tgb200_step_begin(tgb200_mapper* h, void* stream) {
     k_sum_planes<<<(unsigned)ceil_div(vk, 256), 256, 0, s>>>(h->Ypart.p, h->fwd_splits, vk, h->Y.p);
     LAUNCH_CHECK("sum_planes");
   }
+  CKS(join_streams(h, caller));
   h->in_step = true;
   return TGB200_OK;
 }
@@ -673,7 +788,7 @@ static int ensure_history(tgb200_mapper* h, int64_t need, cudaStream_t s) {
   DevBuf<float> nb;
   CKS(nb.alloc((size_t)cap * TGB200_HIST_COLS));
   if (h->hist_len > 0) {
-    CK(cudaStreamSynchronize(s));
+    CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(nb.p, h->hist.p, (size_t)h->hist_len * TGB200_HIST_COLS * sizeof(float), cudaMemcpyDeviceToDevice));
   }
   h->hist.release();
@@ -748,20 +863,30 @@ static int filter_update(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a)
 
 // Staged backward (bf16 mode): dq = bf16(S_ext dY_ext^T - centre) + row-dot partials from the store-only contraction,
 // then one streaming pass does softmax-Jacobian + Adam + the next forward's P.  (mapping_optimizer.py:395-396)
-static int backward_staged(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a) {
+static int backward_staged(tgb200_mapper* h, cudaStream_t s, cudaStream_t su, const AdamScalars& a) {
   if (!h->plan_dp.ready) CKS(tc_dpstore_plan(h->tc, h->plan_dp, h->Sxb.p, h->dYb.p, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
-  TcEpiDpStore epi{h->dq.p, h->Pb.p, h->ld, h->rcenter.p, h->rpart.p, h->N};
-  CKS(tc_dpstore_launch(h->tc, h->plan_dp, epi, 0, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
-  mark(h, s, "tc_gemm_bwd_dp");
-  k_rowdot_finalize_staged<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, 0, h->N, h->lseT, h->inv_zt.p,
-                                                                         h->stats.p, h->rcenter.p, h->rdot.p, h->rowc.p);
-  LAUNCH_CHECK("rowdot_finalize");
-  if (h->constrained) CKS(filter_update(h, s, a));
-  AdamRowsArgs ar{h->M.p, h->m.p, h->v.p, h->dq.p, h->Pb.p, reinterpret_cast<const RowConst*>(h->rowc.p),
-                  h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p, h->ld, h->V, 0, h->N,
-                  h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
-  if (adam_rows_launch(ar, s)) return fail(TGB200_ERR_CUDA, "launch adam_rows: %s", cudaGetErrorString(cudaGetLastError()));
-  mark(h, s, "adam_rows");
+  const bool two_streams = su != s;
+  for (int c = 0; c < h->nchunks; ++c) {
+    const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
+    TcEpiDpStore epi{h->dq.p, h->Pb.p, h->ld, h->rcenter.p, h->rpart.p, h->N};
+    CKS(tc_dpstore_launch(h->tc, h->plan_dp, epi, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_bwd_dp");
+    if (two_streams) {
+      CK(cudaEventRecord(h->ev_g[c], s));
+      CK(cudaStreamWaitEvent(su, h->ev_g[c], 0));
+    }
+    k_rowdot_finalize_staged<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, su>>>(h->rpart.p, h->r_parts, h->N, r0, r1, h->lseT, h->inv_zt.p,
+                                                                               h->stats.p, h->rcenter.p, h->rdot.p, h->rowc.p);
+    { cudaStream_t s = su; LAUNCH_CHECK("rowdot_finalize"); }
+    if (h->constrained) CKS(filter_update(h, su, a));
+    AdamRowsArgs ar{h->M.p, h->m.p, h->v.p, h->dq.p, h->Pb.p, reinterpret_cast<const RowConst*>(h->rowc.p),
+                    h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p, h->ld, h->V, r0, r1,
+                    h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+    if (adam_rows_launch(ar, su)) return fail(TGB200_ERR_CUDA, "launch adam_rows: %s", cudaGetErrorString(cudaGetLastError()));
+    mark(h, su, "adam_rows");
+    if (two_streams) CK(cudaEventRecord(h->ev_a[c], su));
+  }
+  h->a_valid = two_streams;
   // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
   float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
   h->p_state = 2;
@@ -770,10 +895,12 @@ static int backward_staged(tgb200_mapper* h, cudaStream_t s, const AdamScalars& 
 
 extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
   if (!h->in_step) return fail(TGB200_ERR_STATE, "step_end without step_begin");
-  CKS(ensure_history(h, h->hist_len + 1, s));
+  CKS(ensure_history(h, h->hist_len + 1, caller));
+  CKS(fork_streams(h, caller));              // the caller may have all-reduced the exchange buffer on its stream
+  cudaStream_t s = work_stream(h, caller);
   float* hist_row = h->hist.p + (size_t)h->hist_len * TGB200_HIST_COLS;
   // sharded: the caller all-reduced Y (already the sum of every rank's partial planes)
   const bool sharded = h->cfg.n_cells_global != h->N;
@@ -782,7 +909,7 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
   const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
   if (h->staged) {
-    CKS(backward_staged(h, s, a));
+    CKS(backward_staged(h, s, update_stream(h, caller), a));
   } else {
   if (h->tcm) {
     if (!h->plan_rd.ready)
@@ -835,22 +962,81 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
     LAUNCH_CHECK("simt_gemm_bwd_adam");
   }
   }
+  CKS(join_streams(h, caller));
   h->step++;
   h->hist_len++;
   h->in_step = false;
   return TGB200_OK;
 }
 
+// The one exchange of an iteration: sum over ranks of [Y_ext partial | row-scalar partials], in place.
+static int exchange_partials(tgb200_mapper* h, cudaStream_t s) {
+  NcclApi* api = nccl_api(g_err, sizeof(g_err));
+  if (!api) return TGB200_ERR_STATE;
+  const size_t count = (size_t)h->V * h->Ke + kTail;
+  const int r = api->AllReduce(h->Y.p, h->Y.p, count, kNcclFloat32, kNcclSum, h->comm, s);
+  if (r != 0) return fail(TGB200_ERR_CUDA, "ncclAllReduce: %s", api->GetErrorString(r));
+  if (h->timer) { mark(h, s, "nccl_all_reduce"); h->launches--; }   // timed when profiling; not one of OUR kernels
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_comm_unique_id(void* id_out, int64_t cap) {
+  if (!id_out || cap < (int64_t)sizeof(NcclUniqueId)) return fail(TGB200_ERR_INVALID, "id buffer must hold %zu bytes", sizeof(NcclUniqueId));
+  NcclApi* api = nccl_api(g_err, sizeof(g_err));
+  if (!api) return TGB200_ERR_STATE;
+  NcclUniqueId id;
+  const int r = api->GetUniqueId(&id);
+  if (r != 0) return fail(TGB200_ERR_CUDA, "ncclGetUniqueId: %s", api->GetErrorString(r));
+  memcpy(id_out, &id, sizeof(id));
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id, int32_t rank, int32_t world) {
+  if (!h || !unique_id) return fail(TGB200_ERR_INVALID, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(TGB200_ERR_INVALID, "bad rank %d of %d", rank, world);
+  if (h->comm) return fail(TGB200_ERR_STATE, "this handle already has a communicator");
+  NcclApi* api = nccl_api(g_err, sizeof(g_err));
+  if (!api) return TGB200_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  NcclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) return fail(TGB200_ERR_CUDA, "ncclCommInitRank: %s", api->GetErrorString(r));
+  h->comm = comm; h->comm_owned = true; h->comm_rank = rank; h->comm_world = world;
+  return TGB200_OK;
+}
+
+extern "C" int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, int32_t world) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  if (nccl_comm && (world < 1 || rank < 0 || rank >= world)) return fail(TGB200_ERR_INVALID, "bad rank %d of %d", rank, world);
+  if (nccl_comm && !nccl_api(g_err, sizeof(g_err))) return TGB200_ERR_STATE;
+  if (h->comm && h->comm_owned) { if (NcclApi* a = nccl_api(g_err, sizeof(g_err))) a->CommDestroy(h->comm); }
+  h->comm = nccl_comm; h->comm_owned = false; h->comm_rank = rank; h->comm_world = nccl_comm ? world : 1;
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_run(tgb200_mapper* h, int32_t n_steps, float lr, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   if (n_steps < 0) return fail(TGB200_ERR_INVALID, "n_steps < 0");
-  if (h->cfg.n_cells_global != h->N) return fail(TGB200_ERR_STATE, "cell-sharded handle: use step_begin / all-reduce / step_end");
+  const bool sharded = h->cfg.n_cells_global != h->N;
+  if (sharded && !h->comm)
+    return fail(TGB200_ERR_STATE, "cell-sharded handle without a communicator: call tgb200_comm_init_rank / tgb200_set_comm, or drive "
+                                  "step_begin / all-reduce / step_end yourself");
+  CK(cudaSetDevice(h->cfg.device));
   CKS(ensure_history(h, h->hist_len + n_steps, (cudaStream_t)stream));
-  for (int i = 0; i < n_steps; ++i) {
-    CKS(tgb200_step_begin(h, stream));
-    CKS(tgb200_step_end(h, lr, stream));
+  if (n_steps == 0) return TGB200_OK;
+  CKS(fork_streams(h, (cudaStream_t)stream));
+  h->defer_join = true;                      // iterations chain through the handle's own streams and events
+  int st = TGB200_OK;
+  for (int i = 0; i < n_steps && st == TGB200_OK; ++i) {
+    st = tgb200_step_begin(h, stream);
+    if (st == TGB200_OK && sharded) st = exchange_partials(h, work_stream(h, (cudaStream_t)stream));
+    if (st == TGB200_OK) st = tgb200_step_end(h, lr, stream);
   }
-  return TGB200_OK;
+  h->defer_join = false;
+  CKS(join_streams(h, (cudaStream_t)stream));
+  return st;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -988,7 +1174,9 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   CKS(check_ready(h));
   if (h->in_step) return fail(TGB200_ERR_STATE, "validation_terms inside a step");
   if (h->cfg.n_cells_global != h->N) return fail(TGB200_ERR_UNSUPPORTED, "validation_terms on a sharded handle");
-  // _val_loss_fn (:311-356): a second forward on the train matrices
+  // _val_loss_fn (:311-356): a second forward on the train matrices.  bf16 mode: re-run the exact row pass so that the
+  // per-row entropy exists whatever lambda_r is (in steady state it is only carried when the entropy term is on)
+  if (h->bf16) h->p_state = 0;
   CKS(forward_pass(h, s, 1));
   LossParams p = make_loss_params(h);
   DevBuf<float> rowpart, coefAr, coefBr, hist, gnz;
@@ -1053,8 +1241,10 @@ extern "C" int tgb200_profile_step(tgb200_mapper* h, float lr, void* stream, con
   CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(e0, s));
   h->timer = &t;
+  h->serial = true;                          // one stream, one kernel at a time: clean per-kernel durations
   int st = tgb200_step_begin(h, stream);
   if (st == TGB200_OK) st = tgb200_step_end(h, lr, stream);
+  h->serial = false;
   h->timer = nullptr;
   cudaStreamSynchronize(s);
   int cnt = 0;
@@ -1069,6 +1259,26 @@ extern "C" int tgb200_profile_step(tgb200_mapper* h, float lr, void* stream, con
   for (auto e : t.ev) cudaEventDestroy(e);
   *n = cnt;
   return st;
+}
+
+extern "C" int tgb200_debug_timeline(tgb200_mapper* h, int32_t enable, const char** names, int32_t* streams, float* end_ms,
+                                     int32_t cap, int32_t* n) {
+  if (!h) return fail(TGB200_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  if (!enable) {
+    int cnt = 0;
+    for (size_t i = 0; i < h->tl_events.size(); ++i) {
+      float f = 0.f;
+      cudaEventElapsedTime(&f, h->tl_events[0], h->tl_events[i]);
+      if (names && streams && end_ms && cnt < cap) { names[cnt] = h->tl_names[i]; streams[cnt] = h->tl_streams[i]; end_ms[cnt] = f; cnt++; }
+    }
+    if (n) *n = cnt;
+  }
+  for (cudaEvent_t e : h->tl_events) cudaEventDestroy(e);
+  h->tl_events.clear(); h->tl_names.clear(); h->tl_streams.clear();
+  h->timeline_on = enable != 0;
+  return TGB200_OK;
 }
 
 extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* out_host, int64_t cap, int64_t* n) {

@@ -79,6 +79,15 @@ class Engine:
     def step_end(self, lr=0.1, stream=None):
         _lib.check(self._lib.tgb200_step_end(self._h, lr, self._s(stream)))
 
+    def comm_init(self, rank, world, broadcast):
+        """Own NCCL communicator for the cell-sharded tgb200_run: rank 0 creates the 128-byte id (tgb200_comm_unique_id),
+        `broadcast(uint8 ndarray) -> ndarray` carries it to every rank by any means, every rank joins."""
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self._lib.tgb200_comm_unique_id(_lib.ptr(uid), uid.nbytes))
+        uid = np.ascontiguousarray(broadcast(uid), dtype=np.uint8)
+        _lib.check(self._lib.tgb200_comm_init_rank(self._h, _lib.ptr(uid), rank, world))
+
     def exchange_tensor(self):
         import torch
         p, n = ctypes.c_void_p(), ctypes.c_int64()
@@ -132,6 +141,18 @@ class Engine:
         n = ctypes.c_int32()
         _lib.check(self._lib.tgb200_profile_step(self._h, lr, self._s(stream), names, ms, cap, ctypes.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def timeline(self, enable, cap=4096):
+        """tgb200_debug_timeline: enable=True starts recording; enable=False returns [(name, stream, end_ms)]."""
+        if enable:
+            _lib.check(self._lib.tgb200_debug_timeline(self._h, 1, None, None, None, 0, None))
+            return None
+        names = (ctypes.c_char_p * cap)()
+        streams = (ctypes.c_int32 * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = ctypes.c_int32()
+        _lib.check(self._lib.tgb200_debug_timeline(self._h, 0, names, streams, ms, cap, ctypes.byref(n)))
+        return [(names[i].decode(), int(streams[i]), float(ms[i])) for i in range(n.value)]
 
     def algorithmic_cost(self):
         b, f = ctypes.c_double(), ctypes.c_double()

@@ -11,8 +11,11 @@ Additions (keyword-only, all optional):
               "fp32" (FFMA contractions, the cross-check) | "bf16" (plain bf16 operands: throughput mode)
   M0          explicit initial mapping (ndarray N x V); default is the reference draw
   process_group / shard  cell-sharded multi-GPU operation (one process per GPU): every rank passes the
-              full S / M0 and keeps rows shard_rows(N, rank, world)
+              full S (/ M0) and keeps rows shard_rows(N, rank, world); with a NCCL process group the handle gets its own
+              NCCL communicator (tgb200_comm_init_rank) and the per-iteration exchange runs inside tgb200_run
   n_cells_global         pre-sharded variant: S, M0, d_source, ct_encode already hold only this rank's rows
+  train(..., resume=True)  continue with the Adam state of the previous train() call (the reference -- and the default
+              here -- builds a fresh optimizer in every train() call, mapping_optimizer.py:373)
 """
 import ctypes
 
@@ -88,6 +91,23 @@ class _ResultBuffer:
         if self._pinned:
             self._lib.tgb200_host_unpin(_lib.ptr(self.arr))
             self._pinned = False
+
+
+def legacy_normal_rows(random_state, n_rows, n_cols, r0, r1, block_rows=4096):
+    """Rows [r0, r1) of the reference's initial draw `np.random.normal(0, 1, (n_rows, n_cols))` (mapping_optimizer.py:
+    148-150: legacy MT19937, seeded only if `random_state` is truthy) WITHOUT materialising the other rows: the legacy
+    generator has no skip-ahead (polar Box-Muller with rejection), so the stream is consumed block by block and only this
+    rank's rows are kept -- same bits as the full draw, O(block) extra memory instead of 8 bytes x n_rows x n_cols."""
+    if random_state:
+        np.random.seed(seed=random_state)
+    out = np.empty((r1 - r0, n_cols), dtype=np.float32)
+    for b0 in range(0, r1, block_rows):          # rows past r1 are never needed: stop there
+        b1 = min(b0 + block_rows, r1)
+        blk = np.random.normal(0, 1, (b1 - b0, n_cols))
+        lo, hi = max(b0, r0), b1
+        if hi > lo:
+            out[lo - r0:hi - r0] = blk[lo - b0:hi - b0]
+    return out
 
 
 def format_terms(row):
@@ -166,14 +186,10 @@ class Mapper:
             ct_encode = np.ascontiguousarray(np.asarray(ct_encode, dtype=np.float32))
         n_types = ct_encode.shape[1] if (ct_encode is not None and lambda_ct_islands > 0) else 0
 
-        # initial mapping: legacy numpy RNG, float64 draw, f32 cast; seeded only if truthy (:147-157)
-        if M0 is None:
-            if self.random_state:
-                np.random.seed(seed=self.random_state)
-            M0 = np.random.normal(0, 1, (n_rows_given, n_voxels))
-        M0 = np.asarray(M0)
-        if M0.shape != (n_rows_given, n_voxels):
-            raise ValueError("M0 has the wrong shape")
+        if M0 is not None:
+            M0 = np.asarray(M0)
+            if M0.shape != (n_rows_given, n_voxels):
+                raise ValueError("M0 has the wrong shape")
 
         # cell-sharded operation: this rank keeps rows [r0, r1)
         self._rows = (0, n_rows_given)
@@ -187,6 +203,12 @@ class Mapper:
             self._rows = shard_rows(n_cells_global, r, w)
         r0, r1 = self._rows
         sharded = (r1 - r0) != n_cells_global
+        # initial mapping: legacy numpy RNG, float64 draw, f32 cast; seeded only if truthy (:147-157).  A rank of a
+        # sharded run draws the same stream and keeps only its rows (pre-sharded callers pass M0 or get a per-rank draw).
+        if M0 is None:
+            M0 = legacy_normal_rows(self.random_state, n_rows_given, n_voxels, r0, r1)
+        else:
+            M0 = M0[r0:r1]
 
         cfg = _lib.Config()
         cfg.struct_size = ctypes.sizeof(_lib.Config)
@@ -233,15 +255,41 @@ class Mapper:
             if ct_encode is None:
                 raise ValueError("ct_encode is required when lambda_ct_islands > 0")
             _lib.check(L.tgb200_set_ct_encode(h, _lib.ptr(np.ascontiguousarray(ct_encode[r0:r1])), None))
-        M0 = np.ascontiguousarray(M0[r0:r1], dtype=np.float32)
+        M0 = np.ascontiguousarray(M0, dtype=np.float32)
         _lib.check(L.tgb200_set_mapping(h, _lib.ptr(M0), None))
+        del M0
+        self._own_comm = False
+        if sharded and process_group is not None:
+            self._init_comm(process_group)
+
+    def _init_comm(self, pg):
+        """One NCCL communicator per handle (tgb200_comm_init_rank): rank 0 of the group makes the 128-byte unique id,
+        torch.distributed only carries it to the other ranks.  Non-NCCL groups (gloo in the CPU tests) keep the
+        host-driven exchange of tangram_b200.sharded."""
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(pg) != "nccl":
+            return
+        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self._lib.tgb200_comm_unique_id(_lib.ptr(uid), uid.nbytes))
+        t = torch.from_numpy(uid).to(f"cuda:{self._cfg.device}")
+        dist.broadcast(t, src=dist.get_global_rank(pg, 0), group=pg)
+        uid = t.cpu().numpy()
+        _lib.check(self._lib.tgb200_comm_init_rank(self._h, _lib.ptr(uid), rank, world))
+        self._own_comm = True
 
     # ------------------------------------------------------------------------------
+    def release(self):
+        """Free the device state now (M, m, v, operands: ~20 bytes per mapping element) instead of at garbage collection."""
+        if self._h is not None:
+            self._lib.tgb200_destroy(self._h)
+            self._h = None
+
     def __del__(self):
         try:
-            if self._h is not None:
-                self._lib.tgb200_destroy(self._h)
-                self._h = None
+            self.release()
         except Exception:
             pass
 
@@ -266,8 +314,8 @@ class Mapper:
     def _run(self, n_steps, lr):
         if n_steps <= 0:
             return
-        if not self._sharded:
-            _lib.check(self._lib.tgb200_run(self._h, n_steps, lr, None))
+        if not self._sharded or self._own_comm:
+            _lib.check(self._lib.tgb200_run(self._h, n_steps, lr, None))    # sharded: the NCCL exchange is inside
             return
         import torch
         import torch.distributed as dist
@@ -286,11 +334,15 @@ class Mapper:
         sharded_steps(_Eng(), n_steps, lr,
                       lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._pg))   # the one exchange per step
 
-    def train(self, num_epochs, learning_rate=0.1, print_each=100, val_each=None):
-        """mapping_optimizer.py:358-408.  Returns (softmax(M) as (N, V) f32 ndarray, history)."""
+    def train(self, num_epochs, learning_rate=0.1, print_each=100, val_each=None, *, resume=False):
+        """mapping_optimizer.py:358-408.  Returns (softmax(M) as (N, V) f32 ndarray, history).
+        Every call starts a fresh Adam (zero moments, t = 1) like the reference's `torch.optim.Adam([self.M])` at :373;
+        `resume=True` keeps the optimizer state of the previous call instead."""
         import logging
         if print_each:
             logging.info(f"Printing scores every {print_each} epochs.")
+        if not resume:
+            _lib.check(self._lib.tgb200_reset_adam(self._h, None))
         training_history = {key: [] for key in _HIST_KEYS + _VAL_KEYS}
         first = ctypes.c_int64()
         _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
@@ -433,9 +485,11 @@ class MapperConstrained:
         msg = ["{}: {:.3f}".format(n, v) for n, v in zip(names, vals) if not np.isnan(v)]
         return str(msg).replace("[", "").replace("]", "").replace("'", "")
 
-    def train(self, num_epochs, learning_rate=0.1, print_each=100):
-        """mapping_optimizer.py:589-639."""
+    def train(self, num_epochs, learning_rate=0.1, print_each=100, *, resume=False):
+        """mapping_optimizer.py:589-639.  A fresh Adam over [M, F] per call (:607) unless resume=True."""
         keys = ["total_loss", "main_loss", "vg_reg", "kl_reg", "entropy_reg", "count_reg", "lambda_f_reg"]
+        if not resume:
+            _lib.check(self._lib.tgb200_reset_adam(self._h, None))
         first = ctypes.c_int64()
         _lib.check(self._lib.tgb200_history_len(self._h, ctypes.byref(first)))
         first = first.value
@@ -491,5 +545,6 @@ class MapperConstrained:
         return M, self.filter_logits(), step.value
 
 
+MapperConstrained.release = Mapper.release
 MapperConstrained.project = Mapper.project
 MapperConstrained.kernel_launches = Mapper.kernel_launches

@@ -42,10 +42,13 @@ def pp_adatas(adata_sc, adata_sp, genes=None, gene_to_lowercase=True):
     """mapping_utils.py:20-100 (gene intersection + density priors).  The squidpy neighbour
     graph (:95-100) is not computed here: pass it in adata_sp.obsp."""
     for ad in (adata_sc, adata_sp):
-        keep = np.asarray((ad.X != 0).sum(axis=0)).reshape(-1) >= 1        # sc.pp.filter_genes(min_cells=1)
+        # sc.pp.filter_genes(ad, min_cells=1) (:47-48): records var['n_cells'], then drops the all-zero genes IN PLACE --
+        # through AnnData._inplace_subset_var, as scanpy does (assigning a differently shaped X / var to a real AnnData raises)
+        n_cells = np.asarray((ad.X != 0).sum(axis=0)).reshape(-1)
+        ad.var["n_cells"] = n_cells
+        keep = n_cells >= 1
         if not keep.all():
-            sub = ad[:, keep]
-            ad.X, ad.var = sub.X, sub.var
+            ad._inplace_subset_var(keep)
     if genes is None:
         genes = adata_sc.var.index
     if gene_to_lowercase:
@@ -118,9 +121,20 @@ def map_cells_to_space(
     lambda_count=1, lambda_f_reg=1, target_count=None,
     lambda_neighborhood_g1=0, lambda_ct_islands=0, lambda_getis_ord=0, lambda_moran=0, lambda_geary=0,
     random_state=None, verbose=True, density_prior="rna_count_based", precision="bf16x3",
+    process_group=None, gather=False, keep_on_device=False,
 ):
-    """Same contract as the reference (mapping_utils.py:141-428); `device` must be CUDA.
-    `precision` ("bf16x3" parity-grade on tensor cores, default | "fp32" FFMA | "bf16" throughput) is the only added keyword."""
+    """Same contract as the reference (mapping_utils.py:141-428); `device` must be CUDA.  Added keywords:
+    precision       "bf16x3" parity-grade on tensor cores (default) | "fp32" FFMA | "bf16" throughput
+    process_group   torch.distributed group, one process per GPU (mode='cells' only): every rank passes the SAME adata_sc /
+                    adata_sp; the cells are sharded in contiguous blocks (tangram_b200.shard_rows), each rank draws only its
+                    rows of the reference's M0 stream and trains them, one NCCL exchange per epoch.  Each rank returns the
+                    AnnData of ITS cells (obs = that block of adata_sc.obs; `uns['shard_rows']` = (first, last)); the
+                    per-gene scores, the history and `uns` are global and identical on every rank.  gather=True: rank 0
+                    additionally receives the full mapping (all cells) and the other ranks return None.
+    keep_on_device  keep the trained mapper (device state ~20 B per mapping element) attached to the result so that
+                    project_genes contracts on the GPU; default: release it (`adata_map.X` is all project_genes needs)."""
+    if process_group is not None and mode != "cells":
+        raise ValueError("process_group shards the cells axis: only mode='cells' can be sharded (clusters mode has too few rows).")
     lambda_d = _validate_mapping_args(mode, cluster_label, lambda_g1, lambda_d, density_prior, target_count,
                                       lambda_f_reg, lambda_count)
 
@@ -138,6 +152,14 @@ def map_cells_to_space(
         training_genes = cv_train_genes
     else:
         raise ValueError("Given training genes list should be subset of two AnnDatas.")
+
+    if process_group is not None:
+        # pp_adatas builds the gene list through a set (:57-60): its order depends on the process's string hashing, so
+        # the ranks agree on rank 0's order before they slice columns
+        import torch.distributed as dist
+        box = [list(training_genes)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0), group=process_group)
+        training_genes = box[0]
 
     logging.info("Allocate tensors for mapping.")
     S = _dense_f32(adata_sc[:, training_genes].X)                                # :259-275
@@ -201,19 +223,31 @@ def map_cells_to_space(
             learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
     else:
         mapper = mo.Mapper(S=S, G=G, d=None if d is None else np.asarray(d, dtype=np.float32), device=device,
-                           random_state=random_state, precision=precision, **hyperparameters)
+                           random_state=random_state, precision=precision, process_group=process_group, **hyperparameters)
         mapping_matrix, training_history = mapper.train(
             learning_rate=learning_rate, num_epochs=num_epochs, print_each=print_each)
 
     logging.info("Saving results..")
-    adata_map = make_adata(X=mapping_matrix, obs=adata_sc[:, training_genes].obs.copy(),
-                           var=adata_sp[:, training_genes].obs.copy())
+    r0, r1 = getattr(mapper, "_rows", (0, S.shape[0]))
+    obs_map = adata_sc[:, training_genes].obs.copy()
+    if process_group is not None:
+        obs_map = obs_map.iloc[r0:r1]
+    adata_map = make_adata(X=mapping_matrix, obs=obs_map, var=adata_sp[:, training_genes].obs.copy())
+    if process_group is not None:
+        adata_map.uns["shard_rows"] = (int(r0), int(r1))
 
     if mode == "constrained":
         adata_map.obs["F_out"] = F_out                                            # :398-399
 
     # per-gene training score (:401-410): softmax(M)^T S on the device instead of a host GEMM
-    G_predicted = mapper.project(S) if hasattr(mapper, "project") else np.asarray(mapping_matrix).T @ S
+    G_predicted = mapper.project(S[r0:r1])
+    if process_group is not None:             # sum of the ranks' partial projections: the same V x K on every rank
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(G_predicted))
+        t = t.cuda(mapper._cfg.device) if dist.get_backend(process_group) == "nccl" else t
+        dist.all_reduce(t, group=process_group)
+        G_predicted = t.cpu().numpy()
     num = (G * G_predicted).sum(axis=0)
     den = np.linalg.norm(G, axis=0) * np.linalg.norm(G_predicted, axis=0)
     df_cs = pd.DataFrame(num / den, list(training_genes), columns=["train_score"])
@@ -227,8 +261,28 @@ def map_cells_to_space(
     adata_map.uns["train_genes_df"]["sparsity_diff"] = (
         adata_sp[:, training_genes].var.sparsity - adata_sc[:, training_genes].var.sparsity)
     adata_map.uns["training_history"] = training_history
-    try:      # keeps M resident on the device for project_genes (not part of `uns`: stays serialisable)
-        adata_map._tgb200_mapper = mapper
-    except Exception:  # noqa: BLE001
-        pass
+    if keep_on_device and process_group is None:
+        try:      # M stays resident for project_genes (not part of `uns`: the AnnData stays serialisable); mapper.release() frees it
+            adata_map._tgb200_mapper = mapper
+        except Exception:  # noqa: BLE001
+            mapper.release()
+    else:
+        mapper.release()
+    if process_group is not None and gather:
+        adata_map = _gather_mapping(adata_map, adata_sc[:, training_genes].obs.copy(), process_group, device)
     return adata_map
+
+
+def _gather_mapping(adata_map, obs_all, pg, device):
+    """Rank 0 of the group receives every rank's block of rows (gather_object of the host arrays: result packaging, once
+    per mapping) and returns the AnnData over all cells; the other ranks return None."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((adata_map.uns["shard_rows"], np.asarray(adata_map.X)), parts, dst=dist.get_global_rank(pg, 0), group=pg)
+    if rank != 0:
+        return None
+    parts.sort(key=lambda p: p[0][0])
+    full = make_adata(X=np.concatenate([p[1] for p in parts], axis=0), obs=obs_all, var=adata_map.var)
+    full.uns.update({k: v for k, v in adata_map.uns.items() if k != "shard_rows"})
+    return full

@@ -5,7 +5,11 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["cells_default", "cells_nodensity", "cells_regs", "clusters", "cells_spatial"]
-REFERENCE_FILE = "/root/reference/tangram/mapping_optimizer.py"
+# The reference's one-file hot path: the tree itself where it exists (this container), else the verbatim copy that
+# oracle/build_ref.py left in oracle/_ref/ (git-ignored; it travels to the GPU box with the snapshot).
+_REF_CANDIDATES = ["/root/reference/tangram/mapping_optimizer.py",
+                   os.path.join(os.path.dirname(GOLDEN_DIR.rstrip(os.sep)), "..", "oracle", "_ref", "mapping_optimizer.py")]
+REFERENCE_FILE = next((os.path.abspath(p) for p in _REF_CANDIDATES if os.path.exists(p)), _REF_CANDIDATES[0])
 
 
 def load_golden(name):

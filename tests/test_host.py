@@ -136,3 +136,54 @@ def test_mapper_refuses_unsupported_terms_and_cpu():
         tg.Mapper(S, G, adata_map=object())
     with pytest.raises(ValueError, match="B200 GPUs only"):
         tg.Mapper(S, G, device="cpu")
+
+
+def test_legacy_normal_rows_is_a_slice_of_the_reference_draw():
+    """mapping_optimizer.py:148-150: a rank of a sharded run keeps its rows of the SAME legacy stream, bit for bit."""
+    from tangram_b200.mapping_optimizer import legacy_normal_rows
+    np.random.seed(11)
+    full = np.random.normal(0, 1, (53, 17)).astype(np.float32)
+    for r0, r1 in ((0, 53), (0, 20), (20, 41), (41, 53), (7, 8)):
+        assert np.array_equal(legacy_normal_rows(11, 53, 17, r0, r1, block_rows=5), full[r0:r1])
+
+
+class _StrictAnnData(tg.MiniAnnData):
+    """Mimics the shape checks of a real anndata.AnnData: X / var of another shape cannot be assigned."""
+
+    def __setattr__(self, name, value):
+        if name in ("X", "var") and "obs" in self.__dict__ and "var" in self.__dict__ and not self.__dict__.get("_subsetting"):
+            n = value.shape[1] if name == "X" else len(value)
+            if n != len(self.__dict__["var"]):
+                raise ValueError("Data matrix has wrong shape")
+        object.__setattr__(self, name, value)
+
+    def _inplace_subset_var(self, keep):
+        object.__setattr__(self, "_subsetting", True)
+        try:
+            super()._inplace_subset_var(keep)
+        finally:
+            object.__setattr__(self, "_subsetting", False)
+
+
+def test_pp_adatas_filters_all_zero_genes_in_place_like_scanpy():
+    """mapping_utils.py:47-48 (sc.pp.filter_genes(min_cells=1)): works on an AnnData that refuses reshaping assignments,
+    records var['n_cells'], and drops the all-zero gene from X and var together."""
+    rng = np.random.default_rng(1)
+    genes = ["A", "B", "C", "D"]
+    Xs = rng.random((6, 4)).astype(np.float32) + 0.1
+    Xs[:, 2] = 0.0
+    Xs[0, 1] = 0.0
+    ad_sc = _StrictAnnData(X=Xs, obs=pd.DataFrame(index=[f"c{i}" for i in range(6)]), var=pd.DataFrame(index=genes))
+    ad_sp = _StrictAnnData(X=rng.random((5, 4)).astype(np.float32) + 0.1, obs=pd.DataFrame(index=[f"v{i}" for i in range(5)]),
+                           var=pd.DataFrame(index=genes))
+    tg.pp_adatas(ad_sc, ad_sp)
+    assert list(ad_sc.var.index) == ["a", "b", "d"] and ad_sc.X.shape == (6, 3)
+    assert list(ad_sc.var["n_cells"]) == [6, 5, 6] and list(ad_sp.var["n_cells"]) == [5, 5, 5, 5]
+    assert sorted(ad_sc.uns["training_genes"]) == ["a", "b", "d"]
+
+
+def test_process_group_needs_cells_mode():
+    ad_sc, ad_sp = _adatas()
+    tg.pp_adatas(ad_sc, ad_sp)
+    with pytest.raises(ValueError, match="only mode='cells' can be sharded"):
+        tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters", cluster_label="lab", process_group=object())

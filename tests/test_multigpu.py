@@ -37,6 +37,31 @@ for prec, tol in (("fp32", 2e-5), ("bf16", 5e-2)):
     dl = max(abs(float(a) - float(b)) for a, b in zip(hist["total_loss"], oh["total_loss"]))
     print(f"rank {rank} {prec}: rel-Frobenius {err:.3e} max loss diff {dl:.3e}", flush=True)
     assert err < tol and dl < (1e-5 if prec == "fp32" else 1e-3)
+    assert m._own_comm, "NCCL group: the exchange must run inside tgb200_run on the handle's own communicator"
+    m.release()
+# the sharded public entry point: every rank passes the same AnnDatas, gets the AnnData of its cells; rank 0 can gather
+import pandas as pd
+import tangram_b200 as tg
+Na, Va, Ka = 1203, 300, 120
+ia = synthetic_inputs(Na, Va, Ka, seed=9)
+genes = [f"g{i}" for i in range(Ka)]
+ad_sc = tg.MiniAnnData(X=ia["S"].copy(), obs=pd.DataFrame(index=[f"c{i}" for i in range(Na)]), var=pd.DataFrame(index=genes))
+ad_sp = tg.MiniAnnData(X=ia["G"].copy(), obs=pd.DataFrame(index=[f"v{i}" for i in range(Va)]), var=pd.DataFrame(index=genes))
+tg.pp_adatas(ad_sc, ad_sp)
+part = tg.map_cells_to_space(ad_sc, ad_sp, device=f"cuda:{rank}", num_epochs=10, random_state=7, verbose=False, precision="fp32",
+                             process_group=dist.group.WORLD)
+full = tg.map_cells_to_space(ad_sc, ad_sp, device=f"cuda:{rank}", num_epochs=10, random_state=7, verbose=False, precision="fp32",
+                             process_group=dist.group.WORLD, gather=True)
+d = np.asarray(ad_sp.obs["rna_count_based_density"], dtype=np.float32)
+oa = OracleMapper(ia["S"], ia["G"], d=d, lambda_d=1.0, random_state=7)
+ra, _ = oa.train(10, print_each=None)
+a0, a1 = part.uns["shard_rows"]
+assert (a0, a1) == shard_rows(Na, rank, world) and list(part.obs.index) == [f"c{i}" for i in range(a0, a1)]
+assert np.linalg.norm(part.X - ra[a0:a1]) / np.linalg.norm(ra[a0:a1]) < 1e-4
+assert (full is None) == (rank != 0)
+if rank == 0:
+    assert full.X.shape == (Na, Va) and np.linalg.norm(full.X - ra) / np.linalg.norm(ra) < 1e-4
+    assert len(full.uns["train_genes_df"]) == Ka
 dist.barrier()
 dist.destroy_process_group()
 print("MULTIGPU OK", flush=True)

@@ -95,3 +95,19 @@ def test_unseeded_when_random_state_zero():
     b = OracleMapper(inp["S"], inp["G"], random_state=0).M.numpy()
     c = OracleMapper(inp["S"], inp["G"], random_state=0).M.numpy()
     assert np.array_equal(a, b) and not np.array_equal(b, c)
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_FILE), reason="live reference not available")
+def test_second_train_call_restarts_adam_like_the_reference():
+    """mapping_optimizer.py:373: the optimizer is built inside train(), so a second call starts from zero moments."""
+    ref_mod = load_reference_module()
+    inp = synthetic_inputs(60, 25, 12, seed=4)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0, random_state=7)
+    r = ref_mod.Mapper(device="cpu", **kw)
+    r.train(4, print_each=None)
+    r_out, r_hist = r.train(3, print_each=None)
+    o = OracleMapper(**kw)
+    o.train(4, print_each=None)
+    o_out, o_hist = o.train(3, print_each=None)
+    assert rel_fro(o_out, r_out) < 1e-5
+    assert max_rel([float(x) for x in o_hist["total_loss"]], [float(x) for x in r_hist["total_loss"]]) < 1e-5

@@ -3,12 +3,14 @@ reference and against the oracle on seeded inputs.  Tolerances: the north_star a
 relative on the final mapping matrix and on the loss trajectory (fp32 arithmetic)."""
 import contextlib
 import io
+import os
 
 import numpy as np
 import pytest
 
 from oracle.tangram_oracle import OracleMapper, grid_graph, spatial_weights_from_graph, synthetic_inputs
-from tests.helpers import assert_same_print, traj_err, GOLDEN_CASES, load_golden, max_rel, rel_fro
+from tests.helpers import (assert_same_print, traj_err, GOLDEN_CASES, REFERENCE_FILE, load_golden, load_reference_module,
+                           max_rel, rel_fro)
 
 pytestmark = pytest.mark.gpu
 
@@ -140,8 +142,52 @@ def test_determinism_and_resume():
     st = m1.state()
     m2 = _mapper(**kw)
     m2.load_state(*st)
-    c, _ = m2.train(7, print_each=None)
+    c, _ = m2.train(7, print_each=None, resume=True)       # keep the restored Adam state (default: fresh optimizer per train())
     assert np.array_equal(a, c)
+
+
+def test_second_train_call_is_a_fresh_optimizer_like_the_reference():
+    """mapping_optimizer.py:373: Adam is built inside train().  A second train() on the same mapper restarts the moments and
+    the bias correction (oracle pinned to the live reference for this in tests/test_oracle.py); resume=True does not."""
+    inp = synthetic_inputs(700, 200, 90, seed=15)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0)
+    o = OracleMapper(random_state=6, **kw)
+    M0 = o.M.numpy().copy()
+    o.train(4, print_each=None)
+    oo, oh = o.train(3, print_each=None)
+    m = _mapper(M0=M0, **kw)
+    m.train(4, print_each=None)
+    out, hist = m.train(3, print_each=None)
+    assert len(hist["total_loss"]) == 3
+    assert rel_fro(out, oo) < 2e-5
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < 1e-5
+    a, _ = _mapper(M0=M0, **kw).train(7, print_each=None)
+    m2 = _mapper(M0=M0, **kw)
+    m2.train(4, print_each=None)
+    b, _ = m2.train(3, print_each=None, resume=True)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_FILE), reason="reference file not available (oracle/build_ref.py)")
+def test_live_reference_on_the_same_gpu():
+    """The UNMODIFIED reference Mapper with device='cuda' (fp32 cuBLAS SGEMM, autograd, torch.optim.Adam) against the CUDA
+    path from the reference's own initial draw: loss trajectory and final mapping within north_star's 1e-4."""
+    import torch
+    ref = load_reference_module()
+    inp = synthetic_inputs(3000, 700, 300, seed=31)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0)
+    r = ref.Mapper(device="cuda:0", random_state=42, **kw)
+    M0 = r.M.detach().cpu().numpy().copy()
+    rout, rhist = r.train(num_epochs=30, learning_rate=0.1, print_each=None)
+    torch.cuda.synchronize()
+    m = _mapper(M0=M0, **kw)
+    out, hist = m.train(30, print_each=None)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in rhist["total_loss"]]) < 1e-4
+    assert max_rel(hist["main_loss"], rhist["main_loss"]) < 1e-4
+    assert rel_fro(out, rout) < 1e-4
+    # and the default draw of the drop-in class is the reference's draw, bit for bit
+    m2 = _mapper(random_state=42, **kw)
+    assert np.array_equal(m2.state()[0], M0)
 
 
 def test_full_size_properties_config2():
@@ -202,9 +248,17 @@ def test_map_cells_to_space_api_end_to_end():
     o = OracleMapper(S, G, d=np.asarray(ad_sp.obs["rna_count_based_density"], dtype=np.float32), lambda_d=1, random_state=3)
     oo, _ = o.train(20, print_each=None)
     assert rel_fro(ad_map.X, oo) < 1e-4
-    ad_ge = tg.project_genes(ad_map, ad_sc)
+    ad_ge = tg.project_genes(ad_map, ad_sc)                      # default: the mapper was released, host contraction (:368)
+    assert not hasattr(ad_map, "_tgb200_mapper")
     assert ad_ge.X.shape == (V, K) and ad_ge.var["is_training"].all()
     assert rel_fro(ad_ge.X, ad_map.X.T.astype(np.float64) @ np.asarray(ad_sc.X)) < 1e-5
+    # keep_on_device=True: the same projection through tgb200_project on the GPU, then release()
+    ad_map_k = tg.map_cells_to_space(ad_sc, ad_sp, device="cuda:0", num_epochs=20, random_state=3, verbose=False,
+                                     precision=_PREC["value"], keep_on_device=True)
+    assert np.array_equal(ad_map_k.X, ad_map.X)
+    ad_ge_k = tg.project_genes(ad_map_k, ad_sc)
+    assert rel_fro(ad_ge_k.X, ad_ge.X) < 1e-5
+    ad_map_k._tgb200_mapper.release()
     # clusters mode runs and returns one row per cluster
     ad_map_c = tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters", cluster_label="lab", device="cuda:0",
                                      num_epochs=10, random_state=3, verbose=False)

@@ -111,7 +111,7 @@ def test_tc_resume_reinitialises_row_normalisation():
     st = m1.state()
     m2 = Mapper(**kw)
     m2.load_state(*st)
-    b, hb = m2.train(3, print_each=None)
+    b, hb = m2.train(3, print_each=None, resume=True)
     assert rel_fro(b, a) < 5e-3
     assert abs(float(hb["total_loss"][-1]) - float(ha["total_loss"][-1])) < 1e-4
     assert abs(hb["entropy_reg"][-1] - ha["entropy_reg"][-1]) < 1e-3 * abs(ha["entropy_reg"][-1])
@@ -159,7 +159,7 @@ def test_project_multi_chunk_matches_float64(precision):
     assert got.shape == (V, X.shape[1])
     assert rel_fro(got, P.T @ X.astype(np.float64)) < 3e-6
     # projecting must not disturb the optimiser state: 5 + 5 steps == 10 steps of a fresh mapper, bit for bit
-    out_a, hist_a = m.train(5, print_each=None)
+    out_a, hist_a = m.train(5, print_each=None, resume=True)     # same optimizer continues (default: a fresh Adam per train())
     m2 = Mapper(**kw)
     out_b, hist_b = m2.train(10, print_each=None)
     assert np.array_equal(out_a, out_b)
