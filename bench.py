@@ -490,7 +490,7 @@ def main():
             "gemm_rowdot": (2.0 * Nl * V * K, pb * Nl * V + sS * Nl * K + sS * V * K),
             "gemm_bwd_adam": (2.0 * Nl * V * K, 24.0 * Nl * V + sS * Nl * K + sS * V * K),
             "gemm_bwd_dp": (2.0 * Nl * V * K, 4.0 * Nl * V + sS * Nl * K + sS * V * K),      # Pt in (2), dq out (2)
-            "adam_rows": (0.0, 28.0 * Nl * V),                                               # M, m, v in+out, dq in, Pt out
+            "adam_rows": (0.0, 24.0 * Nl * V),                                               # M, v (f32) + m (bf16) in+out, dq in, Pt out
             "softmax_rows": (0.0, (4.0 + pb) * Nl * V),
             "loss_reduce": (0.0, 4.0 * V * K * (1 + 1)),
             "scale_rows": (0.0, 6.0 * Nl * K),

@@ -5,7 +5,7 @@
 //   m, v, M <- Adam(g)                                                (torch.optim.Adam, mapping_optimizer.py:373, :396)
 //   Pt_ij  = exp(Mnew_ij - lse_i)  (bf16) and zt_i = sum_j Pt_ij      (the next forward's operand, see k_row_norm)
 //
-// Pure HBM streaming: 14 B/element in (M, m, v, dq), 14 B/element out (M, m, v, Pt).  One warp owns a row, so the row sums
+// Pure HBM streaming: 12 B/element in (M 4, m 2, v 4, dq 2), 12 B/element out (M 4, m 2, v 4, Pt 2).  One warp owns a row, so the row sums
 // need no partial arrays and are deterministic; every lane moves full 32-byte sectors (LDG.256 / STG.256), 8 columns per
 // lane and iteration, two iterations in flight.
 #pragma once
@@ -15,7 +15,7 @@
 namespace tgb {
 
 struct AdamRowsArgs {
-  float* M; float* m; float* v;          // [rows][ld]
+  float* M; __nv_bfloat16* m; float* v;  // [rows][ld]; the first moment is stored in bf16 (2 + 2 B/element instead of 4 + 4)
   const __nv_bfloat16* dq;               // [rows][ld]
   __nv_bfloat16* Pt;                     // [rows][ld]
   const RowConst* rowc;                  // (lse, r', h) per row
@@ -39,7 +39,25 @@ __device__ __forceinline__ uint4 ldg128_stream(const void* src) {
   return r;
 }
 
-struct AdamRowsLoad { float x[8], m[8], v[8]; uint4 d; };
+struct AdamRowsLoad { float x[8], m[8], v[8]; uint4 d, mq; };
+
+__device__ __forceinline__ void unpack_bf8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(b); f[2 * e + 1] = __high2float(b);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf8(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162 b;
+  b = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t*>(&b);
+  b = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t*>(&b);
+  b = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t*>(&b);
+  b = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t*>(&b);
+  return o;
+}
 
 // PLAIN: default loss (no entropy / L1 / L2) -> packed f32x2 arithmetic, 4 MUFU per element.
 #ifndef TGB_ADAM_MAXNREG
@@ -54,7 +72,7 @@ k_adam_rows(const AdamRowsArgs p) {
   const RowConst rc = p.rowc[row];
   const float lse_l2e = rc.lse * 1.4426950408889634f;
   const size_t base = (size_t)row * p.ld;
-  float* Mr = p.M + base; float* mr = p.m + base; float* vr = p.v + base;
+  float* Mr = p.M + base; __nv_bfloat16* mr = p.m + base; float* vr = p.v + base;
   const __nv_bfloat16* dr = p.dq + base;
   __nv_bfloat16* pr = p.Pt + base;
 
@@ -67,7 +85,7 @@ k_adam_rows(const AdamRowsArgs p) {
   float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
 
   auto load = [&](int c, AdamRowsLoad& L) {
-    ldg256f(Mr + c, L.x); ldg256f(mr + c, L.m); ldg256f(vr + c, L.v);
+    ldg256f(Mr + c, L.x); L.mq = ldg128_stream(mr + c); ldg256f(vr + c, L.v);
     L.d = ldg128_stream(dr + c);
   };
   auto one = [&](float& x, float dq, float& m, float& v) -> float {     // general path, one element; returns Pt
@@ -89,6 +107,7 @@ k_adam_rows(const AdamRowsArgs p) {
   };
   auto process = [&](int c, AdamRowsLoad& L) {
     const uint32_t dw[4] = {L.d.x, L.d.y, L.d.z, L.d.w};
+    unpack_bf8(L.mq, L.m);
     float pt[8];
     if (c + 8 <= p.V) {
       if (PLAIN) {
@@ -122,7 +141,7 @@ k_adam_rows(const AdamRowsArgs p) {
           pt[2 * e + 1] = one(L.x[2 * e + 1], __high2float(d2), L.m[2 * e + 1], L.v[2 * e + 1]);
         }
       }
-      stg256f(Mr + c, L.x); stg256f(mr + c, L.m); stg256f(vr + c, L.v);
+      stg256f(Mr + c, L.x); *reinterpret_cast<uint4*>(mr + c) = pack_bf8(L.m); stg256f(vr + c, L.v);
     } else if (c < p.V) {                   // the ragged group: columns >= V are padding (state stays zero, Pt = 0)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -130,18 +149,12 @@ k_adam_rows(const AdamRowsArgs p) {
         const float dq = (e & 1) ? __high2float(d2) : __low2float(d2);
         pt[e] = (c + e < p.V) ? one(L.x[e], dq, L.m[e], L.v[e]) : 0.f;
       }
-      stg256f(Mr + c, L.x); stg256f(mr + c, L.m); stg256f(vr + c, L.v);
+      stg256f(Mr + c, L.x); *reinterpret_cast<uint4*>(mr + c) = pack_bf8(L.m); stg256f(vr + c, L.v);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) pt[e] = 0.f;
     }
-    uint4 o;
-    __nv_bfloat162 b;
-    b = __floats2bfloat162_rn(pt[0], pt[1]); o.x = *reinterpret_cast<uint32_t*>(&b);
-    b = __floats2bfloat162_rn(pt[2], pt[3]); o.y = *reinterpret_cast<uint32_t*>(&b);
-    b = __floats2bfloat162_rn(pt[4], pt[5]); o.z = *reinterpret_cast<uint32_t*>(&b);
-    b = __floats2bfloat162_rn(pt[6], pt[7]); o.w = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint4*>(pr + c) = o;
+    *reinterpret_cast<uint4*>(pr + c) = pack_bf8(pt);
   };
 
   // ld is a multiple of 64: every 8-column group of the row is inside the allocation

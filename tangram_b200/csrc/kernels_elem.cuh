@@ -520,8 +520,8 @@ k_loss_scalars(LossParams p, int nchunk, int ncolchunk, float* __restrict__ hist
 // tensor-core path, bf16.
 __global__ void __launch_bounds__(kLossCols)
 k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ dYb, Split3 split) {
-  const int k0 = (blockIdx.x * kLossCols + threadIdx.x) * kLossVec;     // four columns per thread
-  const int j = blockIdx.y;
+  const int k0 = (blockIdx.y * kLossCols + threadIdx.x) * kLossVec;     // four columns per thread
+  const int j = blockIdx.x;                  // voxels on gridDim.x (2^31 - 1): gridDim.y stops at 65535, real sections have more spots
   if (k0 >= p.Ke) return;
   const size_t o = (size_t)j * p.Ke + k0;
   const float4 y4 = *reinterpret_cast<const float4*>(p.Y + o);
@@ -574,8 +574,8 @@ k_dy_assemble(LossParams p, float* __restrict__ dY, __nv_bfloat16* __restrict__ 
 // One-time helpers (constants of the loss, input packing, init).
 // ------------------------------------------------------------------------------------
 __global__ void k_spmm(int V, int K, int Ke, Csr op, const float* __restrict__ X, float* __restrict__ Z) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
+  const int j = blockIdx.x;                  // voxels on gridDim.x: no 65535 limit
   if (k >= Ke) return;
   float z = 0.f;
   if (k < K)
@@ -636,6 +636,10 @@ __global__ void k_fill_density_cols(float* __restrict__ Sx, int rows, int ld, in
 __global__ void k_f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 // M0 ~ N(0,1) on device (Philox4x32-10), pad columns zero.  Throughput runs only; the
 // reference draw (:150) is a host MT19937 float64 draw and is uploaded via set_mapping.

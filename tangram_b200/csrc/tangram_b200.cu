@@ -129,6 +129,9 @@ struct tgb200_mapper {
   // two contractions per iteration instead of three (no separate row-dot GEMM)
   bool staged = false;
   DevBuf<__nv_bfloat16> dq;     // N x ld
+  DevBuf<__nv_bfloat16> mb;     // N x ld: Adam's first moment in bf16 (staged mode only; `m` is then not allocated).  It is an
+                                // exponential average with a 10-iteration memory: bf16 rounding noise does not accumulate, and
+                                // next to bf16 operands it is invisible in every parity metric; v stays fp32.
   DevBuf<float> rcenter;        // per row: last iteration's row-dot, the centre dq is stored relative to
   // Pipelining of the staged backward over cell chunks (rows [chunk_row[c], chunk_row[c+1]), multiples of 256):
   //   hi (high-priority stream): forward(c) ... loss ... backward contraction(c)        -- tensor-core bound
@@ -138,9 +141,13 @@ struct tgb200_mapper {
   // start of an API call and joins hi + lo at its end (tgb200_run joins once, after its last iteration).
   bool pipelined = false;
   int nchunks = 1, chunk_row[9] = {0};
-  cudaStream_t hi = nullptr, lo = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join_hi = nullptr, ev_join_lo = nullptr, ev_g[8] = {}, ev_a[8] = {};
+  cudaStream_t hi = nullptr, lo = nullptr, sf = nullptr;     // sf: the NEXT iteration's forward chunks (see backward_staged)
+  cudaEvent_t ev_fork = nullptr, ev_join_hi = nullptr, ev_join_lo = nullptr, ev_join_sf = nullptr, ev_loss = nullptr;
+  cudaEvent_t ev_g[8] = {}, ev_a[8] = {}, ev_f[8] = {};
   bool a_valid = false;         // ev_a[] were recorded by an earlier step_end and guard the rows of the next forward
+  bool prefetch_next = false;   // tgb200_run, not its last iteration: issue the NEXT forward's chunks between this backward's chunks
+  bool fwd_ahead = false;       // ... and they have been issued: the next step_begin skips its chunk loop
+  bool l2_persist = false;      // dY_ext pinned in L2 (access-policy window on the contraction stream)
   bool defer_join = false;      // inside tgb200_run: no fork / join between its iterations
   bool serial = false;          // tgb200_profile_step: everything on the caller's stream, one kernel at a time
   // diagnostics (tgb200_debug_timeline): completion time of every launch on its stream
@@ -156,8 +163,10 @@ struct tgb200_mapper {
     if (comm && comm_owned) { char e[64]; if (NcclApi* a = nccl_api(e, sizeof(e))) a->CommDestroy(comm); }
     if (hi) cudaStreamDestroy(hi);
     if (lo) cudaStreamDestroy(lo);
-    for (cudaEvent_t e : {ev_fork, ev_join_hi, ev_join_lo}) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 8; ++i) { if (ev_g[i]) cudaEventDestroy(ev_g[i]); if (ev_a[i]) cudaEventDestroy(ev_a[i]); }
+    if (sf) cudaStreamDestroy(sf);
+    for (cudaEvent_t e : {ev_fork, ev_join_hi, ev_join_lo, ev_join_sf, ev_loss}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 8; ++i)
+      for (cudaEvent_t e : {ev_g[i], ev_a[i], ev_f[i]}) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -173,7 +182,7 @@ static void mark(tgb200_mapper* h, cudaStream_t s, const char* name) {
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
     h->tl_names.push_back(name);
-    h->tl_streams.push_back(s == h->hi ? 1 : (s == h->lo ? 2 : 0));
+    h->tl_streams.push_back(s == h->hi ? 1 : (s == h->lo ? 2 : (s == h->sf ? 3 : 0)));
     h->tl_events.push_back(e);
   }
   if (h->timer) {
@@ -275,10 +284,13 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   const size_t nv = (size_t)h->N * h->ld, vk = (size_t)h->V * h->Ke;
   int st = TGB200_OK;
   auto A = [&](int s) { if (st == TGB200_OK) st = s; };
-  A(h->M.alloc(nv)); A(h->m.alloc(nv)); A(h->v.alloc(nv));
   if (h->bf16) {
     const char* bw = getenv("TGB200_BWD");          // "fused": the round-1 three-contraction pipeline (A/B measurements)
     h->staged = !(bw && strcmp(bw, "fused") == 0);
+  }
+  A(h->M.alloc(nv)); A(h->v.alloc(nv));
+  if (h->staged) A(h->mb.alloc(nv)); else A(h->m.alloc(nv));
+  if (h->bf16) {
     h->z_parts = h->staged ? 1 : tc_bwd_col_parts(h->V);
     A(h->Sxs.alloc((size_t)h->N * h->Ke)); A(h->lse0.alloc(h->N)); A(h->lse1.alloc(h->N)); A(h->inv_zt.alloc(h->N));
     A(h->zpart.alloc((size_t)h->z_parts * h->N));
@@ -295,8 +307,9 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   A(h->d.alloc(h->V)); A(h->dsrc.alloc(h->N));
   A(h->stats.alloc(h->N)); A(h->rowaux.alloc((size_t)2 * h->N)); A(h->rdot.alloc(h->N));
   if (h->staged) {
-    // cell chunks of the pipelined backward: 4 from 32k cells up (each chunk still fills the GPU several times over)
-    int nc = (h->N >= 32768 && !h->constrained) ? 4 : 1;
+    // cell chunks of the pipelined backward: 4 from 32k cells up, 2 from 8k (a rank of an 8-way sharded 100k-cell run):
+    // each chunk still fills the GPU several times over
+    int nc = h->N >= 32768 ? 4 : (h->N >= 8192 ? 2 : 1);
     if (const char* e = getenv("TGB200_CHUNKS")) nc = atoi(e);
     if (nc < 1) nc = 1;
     if (nc > 8) nc = 8;
@@ -306,15 +319,20 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     for (int c = 0; c <= nc; ++c) h->chunk_row[c] = c == nc ? h->N : (int)round_up((int64_t)c * h->N / nc, 256);
     int lo_p = 0, hi_p = 0;
     cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    // priorities: backward contractions (they feed the streaming update) > next forward's chunks > the update itself
+    const int mid_p = hi_p < lo_p ? hi_p + 1 : lo_p;
     bool ok = cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, hi_p) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&h->sf, cudaStreamNonBlocking, mid_p) == cudaSuccess &&
               cudaStreamCreateWithPriority(&h->lo, cudaStreamNonBlocking, lo_p) == cudaSuccess;
-    cudaEvent_t* evs[3] = {&h->ev_fork, &h->ev_join_hi, &h->ev_join_lo};
+    cudaEvent_t* evs[5] = {&h->ev_fork, &h->ev_join_hi, &h->ev_join_lo, &h->ev_join_sf, &h->ev_loss};
     for (auto e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
     for (int c = 0; c < 8; ++c)
       ok = ok && cudaEventCreateWithFlags(&h->ev_g[c], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&h->ev_a[c], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&h->ev_a[c], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_f[c], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) A(fail(TGB200_ERR_CUDA, "stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
     h->pipelined = ok;
+    h->l2_persist = getenv("TGB200_L2_PERSIST") && atoi(getenv("TGB200_L2_PERSIST")) != 0;
   }
   // forward split over cells so that the grid covers the 148 SMs (deterministic partial planes)
   {
@@ -362,6 +380,22 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   if (cfg->lambda_ct_islands > 0.f) {
     h->n_ct_blocks = (int)ceil_div((int64_t)h->V * h->T, 256);
     A(h->H.alloc((size_t)h->V * h->T)); A(h->ctpart.alloc(h->n_ct_blocks));
+  }
+  if (st == TGB200_OK && h->l2_persist && h->pipelined) {
+    // keep dY_ext (the B operand every backward tile re-reads) resident in L2 while the state streams through it
+    const size_t bytes = (size_t)h->V * h->Ke * sizeof(__nv_bfloat16);
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
+    const size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.base_ptr = h->dYb.p;
+    attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    attr.accessPolicyWindow.hitRatio = want >= bytes ? 1.0f : (float)want / (float)bytes;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(h->hi, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { (void)cudaGetLastError(); h->l2_persist = false; }
   }
   if (st == TGB200_OK && h->tcm) st = tc_init(h->tc, g_err, sizeof(g_err));
   if (st != TGB200_OK) { delete h; return st; }
@@ -413,7 +447,7 @@ static int fill_density_cols(tgb200_mapper* h, cudaStream_t s) {
 
 static int precompute_graph_constants(tgb200_mapper* h, cudaStream_t s) {
   if (!h->have_expr) return TGB200_OK;
-  dim3 grid((unsigned)ceil_div(h->Ke, 128), h->V);
+  dim3 grid(h->V, (unsigned)ceil_div(h->Ke, 128));      // voxels on x: gridDim.y is limited to 65535
   if (h->cfg.lambda_neighborhood_g1 > 0.f && h->W.set) {
     k_spmm<<<grid, 128, 0, s>>>(h->V, h->K, h->Ke, h->W.view(), h->G.p, h->WG.p);
     LAUNCH_CHECK("spmm");
@@ -524,13 +558,15 @@ extern "C" int tgb200_set_graph(tgb200_mapper* h, int which, const int32_t* indp
 }
 
 static int reset_optimizer(tgb200_mapper* h, cudaStream_t s) {
-  CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
+  if (h->staged) CK(cudaMemsetAsync(h->mb.p, 0, h->mb.n * sizeof(__nv_bfloat16), s));
+  else CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
   CK(cudaMemsetAsync(h->v.p, 0, h->v.n * sizeof(float), s));
   if (h->staged) CK(cudaMemsetAsync(h->rcenter.p, 0, h->rcenter.n * sizeof(float), s));
   h->step = 0;
   h->hist_len = 0;
   h->in_step = false;
   h->p_state = 0;
+  h->fwd_ahead = false;
   return TGB200_OK;
 }
 
@@ -541,7 +577,8 @@ extern "C" int tgb200_reset_adam(tgb200_mapper* h, void* stream) {
   if (h->in_step) return fail(TGB200_ERR_STATE, "reset_adam inside a step");
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
+  if (h->staged) CK(cudaMemsetAsync(h->mb.p, 0, h->mb.n * sizeof(__nv_bfloat16), s));
+  else CK(cudaMemsetAsync(h->m.p, 0, h->m.n * sizeof(float), s));
   CK(cudaMemsetAsync(h->v.p, 0, h->v.n * sizeof(float), s));
   if (h->constrained) {
     CK(cudaMemsetAsync(h->mF.p, 0, h->mF.n * sizeof(float), s));
@@ -610,13 +647,17 @@ extern "C" int tgb200_init_mapping_normal_rows(tgb200_mapper* h, uint64_t seed, 
 }
 
 // ---------------------------------------------------------------------------------------
+// rows [row0, row0 + nrows) of M -> P (row 0 of `P` is row `row0` of the mapping when P is a scratch block)
 template <typename PT>
 static int launch_softmax_rows(tgb200_mapper* h, cudaStream_t s, PT* P, int want_entropy, float* rowaux,
-                               Split3 split = Split3{nullptr, 0}) {
+                               Split3 split = Split3{nullptr, 0}, int row0 = 0, int nrows = -1) {
   const int nvec = h->ld / 4;
+  if (nrows < 0) nrows = h->N - row0;
+  const float* Mp = h->M.p + (size_t)row0 * h->ld;
+  RowStat* st = h->stats.p + row0;
   constexpr int TH = 256;
 #define SMX(ITEMS)                                                                                  \
-  k_softmax_rows<PT, TH, ITEMS><<<h->N, TH, 0, s>>>(h->M.p, h->ld, h->V, P, h->ld, h->stats.p, rowaux, want_entropy, split)
+  k_softmax_rows<PT, TH, ITEMS><<<nrows, TH, 0, s>>>(Mp, h->ld, h->V, P, h->ld, st, rowaux, want_entropy, split)
   if (nvec <= TH * 1) SMX(1);
   else if (nvec <= TH * 2) SMX(2);
   else if (nvec <= TH * 4) SMX(4);
@@ -679,6 +720,31 @@ static int join_streams(tgb200_mapper* h, cudaStream_t s) {
   CK(cudaStreamWaitEvent(s, h->ev_join_hi, 0));
   CK(cudaEventRecord(h->ev_join_lo, h->lo));
   CK(cudaStreamWaitEvent(s, h->ev_join_lo, 0));
+  CK(cudaEventRecord(h->ev_join_sf, h->sf));
+  CK(cudaStreamWaitEvent(s, h->ev_join_sf, 0));
+  return TGB200_OK;
+}
+
+// bf16 mode, cells of chunk c: exact row statistics from the sums the update left (k_row_norm), the scaled forward operand,
+// and -- when the forward is chunked -- this chunk's partial plane of Y_ext.  `lseA` / `lseT` as they are for THAT forward.
+static int forward_chunk(tgb200_mapper* h, cudaStream_t s, int c, int fresh, const float* lseA, float* lseT) {
+  float* rowaux = needs_rowaux(h->cfg) ? h->rowaux.p : nullptr;
+  if (!h->plan_fwd.ready)
+    CKS(tc_forward_plan(h->tc, h->plan_fwd, h->Pb.p, (size_t)h->N * h->ld, h->Sxs.p, (size_t)h->N * h->Ke, 1, h->N, h->V, h->Ke, h->ld,
+                        g_err, sizeof(g_err)));
+  const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
+  // rows of this chunk: the streaming Adam kernel of the previous iteration must have written their P and row sums
+  if (h->a_valid && h->pipelined && !h->serial) CK(cudaStreamWaitEvent(s, h->ev_a[c], 0));
+  k_row_norm<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, s>>>(h->N, fresh, h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p, h->z_parts,
+                                                             lseA, lseT, h->inv_zt.p, h->stats.p, rowaux, r0, r1);
+  LAUNCH_CHECK("row_norm");
+  const long long nq = (long long)(r1 - r0) * (h->Ke / 4);
+  k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, r0, r1, h->Ke, h->Sxs.p);
+  LAUNCH_CHECK("scale_rows");
+  if (h->nchunks > 1) {
+    CKS(tc_forward_launch_rows(h->tc, h->plan_fwd, h->Ypart.p + (size_t)c * h->V * h->Ke, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    mark(h, s, "tc_gemm_fwd");
+  }
   return TGB200_OK;
 }
 
@@ -692,23 +758,12 @@ static int forward_pass(tgb200_mapper* h, cudaStream_t s, int want_entropy) {
       CKS(launch_softmax_rows<__nv_bfloat16>(h, s, h->Pb.p, 1, rowaux));
       h->p_state = 1;
     }
-    if (!h->plan_fwd.ready)
-      CKS(tc_forward_plan(h->tc, h->plan_fwd, h->Pb.p, (size_t)h->N * h->ld, h->Sxs.p, (size_t)h->N * h->Ke, 1, h->N, h->V, h->Ke, h->ld,
-                          g_err, sizeof(g_err)));
-    for (int c = 0; c < h->nchunks; ++c) {
-      const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
-      // rows of this chunk: the streaming Adam kernel of the previous iteration must have written their P and row sums
-      if (h->a_valid && h->pipelined && !h->serial) CK(cudaStreamWaitEvent(s, h->ev_a[c], 0));
-      k_row_norm<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, s>>>(h->N, h->p_state == 1 ? 1 : 0, h->zpart.p, h->pxpart.p, h->l1part.p,
-                                                                 h->l2part.p, h->z_parts, h->lseA, h->lseT, h->inv_zt.p, h->stats.p, rowaux, r0, r1);
-      LAUNCH_CHECK("row_norm");
-      const long long nq = (long long)(r1 - r0) * (h->Ke / 4);
-      k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, r0, r1, h->Ke, h->Sxs.p);
-      LAUNCH_CHECK("scale_rows");
-      if (h->nchunks > 1) {
-        CKS(tc_forward_launch_rows(h->tc, h->plan_fwd, h->Ypart.p + (size_t)c * h->V * h->Ke, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
-        mark(h, s, "tc_gemm_fwd");
-      }
+    if (h->fwd_ahead) {           // issued by the previous iteration's backward (forward_chunk under the streaming Adam kernel)
+      h->fwd_ahead = false;
+      for (int c = 0; c < h->nchunks; ++c) CK(cudaStreamWaitEvent(s, h->ev_f[c], 0));
+      if (h->nchunks > 1) return TGB200_OK;
+    } else {
+      for (int c = 0; c < h->nchunks; ++c) CKS(forward_chunk(h, s, c, h->p_state == 1 ? 1 : 0, h->lseA, h->lseT));
     }
     if (h->nchunks > 1) return TGB200_OK;
   } else if (h->x3) {
@@ -831,7 +886,7 @@ static int loss_stage(tgb200_mapper* h, cudaStream_t s, float* hist_row, bool re
   }
   k_loss_scalars<<<1, 1024, 0, s>>>(p, 1, h->nredchunk, hist_row);
   LAUNCH_CHECK("loss_scalars");
-  dim3 dgrid(h->nredchunk, h->V);
+  dim3 dgrid(h->V, h->nredchunk);                       // voxels on x: gridDim.y is limited to 65535
   // the tensor-core path consumes only the bf16 copy of dY_ext
   k_dy_assemble<<<dgrid, kLossCols, 0, s>>>(p, h->tcm ? nullptr : h->dY.p, h->bf16 ? h->dYb.p : nullptr,
                                             h->x3 ? Split3{h->dYb.p, (size_t)h->V * h->Ke} : Split3{nullptr, 0});
@@ -866,6 +921,7 @@ static int filter_update(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a)
 static int backward_staged(tgb200_mapper* h, cudaStream_t s, cudaStream_t su, const AdamScalars& a) {
   if (!h->plan_dp.ready) CKS(tc_dpstore_plan(h->tc, h->plan_dp, h->Sxb.p, h->dYb.p, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
   const bool two_streams = su != s;
+  const bool prefetch = two_streams && h->prefetch_next && h->nchunks > 1 && !h->constrained;
   for (int c = 0; c < h->nchunks; ++c) {
     const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
     TcEpiDpStore epi{h->dq.p, h->Pb.p, h->ld, h->rcenter.p, h->rpart.p, h->N};
@@ -879,14 +935,24 @@ static int backward_staged(tgb200_mapper* h, cudaStream_t s, cudaStream_t su, co
                                                                                h->stats.p, h->rcenter.p, h->rdot.p, h->rowc.p);
     { cudaStream_t s = su; LAUNCH_CHECK("rowdot_finalize"); }
     if (h->constrained) CKS(filter_update(h, su, a));
-    AdamRowsArgs ar{h->M.p, h->m.p, h->v.p, h->dq.p, h->Pb.p, reinterpret_cast<const RowConst*>(h->rowc.p),
+    AdamRowsArgs ar{h->M.p, h->mb.p, h->v.p, h->dq.p, h->Pb.p, reinterpret_cast<const RowConst*>(h->rowc.p),
                     h->zpart.p, h->pxpart.p, h->l1part.p, h->l2part.p, h->ld, h->V, r0, r1,
                     h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
     if (adam_rows_launch(ar, su)) return fail(TGB200_ERR_CUDA, "launch adam_rows: %s", cudaGetErrorString(cudaGetLastError()));
     mark(h, su, "adam_rows");
     if (two_streams) CK(cudaEventRecord(h->ev_a[c], su));
+    h->a_valid = two_streams;
+    // The next iteration's forward for this chunk goes to a third stream as soon as its rows are updated: the backward
+    // contractions G(c+1..) run ahead on `s` (they feed the update), the update stream is never without tensor-core work
+    // beside it, and nothing queues behind a kernel that still waits for the update.
+    // (lseT of this iteration is the offset the new P was written with = lseA of the next; the other buffer is free.)
+    if (prefetch) {
+      if (c == 0) CK(cudaStreamWaitEvent(h->sf, h->ev_loss, 0));      // the partial planes of Y_ext were consumed by this iteration's loss
+      CKS(forward_chunk(h, h->sf, c, 0, h->lseT, h->lseA));            // waits for ev_a[c]
+      CK(cudaEventRecord(h->ev_f[c], h->sf));
+    }
   }
-  h->a_valid = two_streams;
+  h->fwd_ahead = prefetch;
   // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
   float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
   h->p_state = 2;
@@ -905,6 +971,7 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   // sharded: the caller all-reduced Y (already the sum of every rank's partial planes)
   const bool sharded = h->cfg.n_cells_global != h->N;
   CKS(loss_stage(h, s, hist_row, !sharded));
+  if (h->pipelined && !h->serial) CK(cudaEventRecord(h->ev_loss, s));
 
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
   const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
@@ -1029,12 +1096,15 @@ extern "C" int tgb200_run(tgb200_mapper* h, int32_t n_steps, float lr, void* str
   CKS(fork_streams(h, (cudaStream_t)stream));
   h->defer_join = true;                      // iterations chain through the handle's own streams and events
   int st = TGB200_OK;
+  static const bool kPrefetch = !(getenv("TGB200_PREFETCH_FWD") && atoi(getenv("TGB200_PREFETCH_FWD")) == 0);
   for (int i = 0; i < n_steps && st == TGB200_OK; ++i) {
+    h->prefetch_next = kPrefetch && i + 1 < n_steps;
     st = tgb200_step_begin(h, stream);
     if (st == TGB200_OK && sharded) st = exchange_partials(h, work_stream(h, (cudaStream_t)stream));
     if (st == TGB200_OK) st = tgb200_step_end(h, lr, stream);
   }
   h->defer_join = false;
+  h->prefetch_next = false;
   CKS(join_streams(h, (cudaStream_t)stream));
   return st;
 }
@@ -1062,12 +1132,26 @@ extern "C" int tgb200_get_mapping(tgb200_mapper* h, float* out, void* stream) {
   if (!h->have_mapping) return fail(TGB200_ERR_STATE, "no mapping set");
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->cfg.device));
+  // softmax(M) in fp32 (:406-407), through device memory the iterations leave idle between calls -- no allocation here:
+  //   fp32 mode          Pf (the forward operand itself)
+  //   bf16x3 mode        the three bf16 P planes (6 B/element, rewritten by every forward pass)
+  //   bf16 staged mode   dq (2 B/element: half of the rows at a time)
+  const size_t nv = (size_t)h->N * h->ld;
   DevBuf<float> tmp;
-  float* P = h->Pf.p;
-  if (h->tcm) { CKS(tmp.alloc((size_t)h->N * h->ld, false)); P = tmp.p; }
-  CKS(launch_softmax_rows<float>(h, s, P, 0, nullptr));      // :406-407
-  CK(cudaMemcpy2DAsync(out, (size_t)h->V * sizeof(float), P, (size_t)h->ld * sizeof(float),
-                       (size_t)h->V * sizeof(float), h->N, cudaMemcpyDefault, s));
+  float* scratch = h->Pf.p;
+  size_t cap_elems = nv;
+  if (h->x3) { scratch = reinterpret_cast<float*>(h->Pb.p); cap_elems = 3 * nv / 2; }
+  else if (h->staged) { scratch = reinterpret_cast<float*>(h->dq.p); cap_elems = nv / 2; }
+  else if (h->tcm) { CKS(tmp.alloc(nv, false)); scratch = tmp.p; }
+  int blk = (int)(cap_elems / (size_t)h->ld);
+  if (blk > h->N) blk = h->N;
+  if (blk < 1) { CKS(tmp.alloc((size_t)h->ld, false)); scratch = tmp.p; blk = 1; }     // one-row mapping in staged mode
+  for (int r0 = 0; r0 < h->N; r0 += blk) {
+    const int nr = h->N - r0 < blk ? h->N - r0 : blk;
+    CKS(launch_softmax_rows<float>(h, s, scratch, 0, nullptr, Split3{nullptr, 0}, r0, nr));
+    CK(cudaMemcpy2DAsync(out + (size_t)r0 * h->V, (size_t)h->V * sizeof(float), scratch, (size_t)h->ld * sizeof(float),
+                         (size_t)h->V * sizeof(float), nr, cudaMemcpyDefault, s));
+  }
   CK(cudaStreamSynchronize(s));
   return TGB200_OK;
 }
@@ -1078,7 +1162,20 @@ extern "C" int tgb200_get_state(tgb200_mapper* h, float* M, float* m, float* v, 
   CK(cudaSetDevice(h->cfg.device));
   const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
   if (M) CK(cudaMemcpy2DAsync(M, w, h->M.p, pitch, w, h->N, cudaMemcpyDefault, s));
-  if (m) CK(cudaMemcpy2DAsync(m, w, h->m.p, pitch, w, h->N, cudaMemcpyDefault, s));
+  if (m && !h->staged) CK(cudaMemcpy2DAsync(m, w, h->m.p, pitch, w, h->N, cudaMemcpyDefault, s));
+  if (m && h->staged) {       // bf16 first moment -> fp32 for the caller, through the idle dq buffer (half of the rows at a time)
+    float* scratch = reinterpret_cast<float*>(h->dq.p);
+    DevBuf<float> one_row;
+    int blk = h->N / 2;
+    if (blk < 1) { CKS(one_row.alloc((size_t)h->ld, false)); scratch = one_row.p; blk = 1; }
+    for (int r0 = 0; r0 < h->N; r0 += blk) {
+      const int nr = h->N - r0 < blk ? h->N - r0 : blk;
+      const long long n = (long long)nr * h->ld;
+      k_bf16_to_f32<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(h->mb.p + (size_t)r0 * h->ld, scratch, n);
+      LAUNCH_CHECK("bf16_to_f32");
+      CK(cudaMemcpy2DAsync(m + (size_t)r0 * h->V, w, scratch, pitch, w, nr, cudaMemcpyDefault, s));
+    }
+  }
   if (v) CK(cudaMemcpy2DAsync(v, w, h->v.p, pitch, w, h->N, cudaMemcpyDefault, s));
   if (step) *step = h->step;
   CK(cudaStreamSynchronize(s));
@@ -1093,9 +1190,24 @@ extern "C" int tgb200_set_state(tgb200_mapper* h, const float* M, const float* m
   const size_t w = (size_t)h->V * sizeof(float), pitch = (size_t)h->ld * sizeof(float);
   if (M) {
     CK(cudaMemcpy2DAsync(h->M.p, pitch, M, w, w, h->N, cudaMemcpyDefault, s)); h->have_mapping = true; h->p_state = 0;
+    h->fwd_ahead = false;
     if (h->staged) CK(cudaMemsetAsync(h->rcenter.p, 0, h->rcenter.n * sizeof(float), s));
   }
-  if (m) CK(cudaMemcpy2DAsync(h->m.p, pitch, m, w, w, h->N, cudaMemcpyDefault, s));
+  if (m && !h->staged) CK(cudaMemcpy2DAsync(h->m.p, pitch, m, w, w, h->N, cudaMemcpyDefault, s));
+  if (m && h->staged) {       // fp32 from the caller -> bf16 (exact for values that came out of tgb200_get_state)
+    float* scratch = reinterpret_cast<float*>(h->dq.p);
+    DevBuf<float> one_row;
+    int blk = h->N / 2;
+    if (blk < 1) { CKS(one_row.alloc((size_t)h->ld)); scratch = one_row.p; blk = 1; }
+    for (int r0 = 0; r0 < h->N; r0 += blk) {
+      const int nr = h->N - r0 < blk ? h->N - r0 : blk;
+      const long long n = (long long)nr * h->ld;
+      CK(cudaMemsetAsync(scratch, 0, (size_t)n * sizeof(float), s));            // pad columns stay zero
+      CK(cudaMemcpy2DAsync(scratch, pitch, m + (size_t)r0 * h->V, w, w, nr, cudaMemcpyDefault, s));
+      k_f32_to_bf16<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scratch, h->mb.p + (size_t)r0 * h->ld, n);
+      LAUNCH_CHECK("f32_to_bf16");
+    }
+  }
   if (v) CK(cudaMemcpy2DAsync(h->v.p, pitch, v, w, w, h->N, cudaMemcpyDefault, s));
   h->step = step;
   CK(cudaStreamSynchronize(s));
@@ -1176,7 +1288,7 @@ extern "C" int tgb200_validation_terms(tgb200_mapper* h, float* out4, void* stre
   if (h->cfg.n_cells_global != h->N) return fail(TGB200_ERR_UNSUPPORTED, "validation_terms on a sharded handle");
   // _val_loss_fn (:311-356): a second forward on the train matrices.  bf16 mode: re-run the exact row pass so that the
   // per-row entropy exists whatever lambda_r is (in steady state it is only carried when the entropy term is on)
-  if (h->bf16) h->p_state = 0;
+  if (h->bf16) { h->p_state = 0; h->fwd_ahead = false; }
   CKS(forward_pass(h, s, 1));
   LossParams p = make_loss_params(h);
   DevBuf<float> rowpart, coefAr, coefBr, hist, gnz;
@@ -1370,7 +1482,9 @@ extern "C" int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, doub
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   const double N = h->N, V = h->V, K = h->K, T = h->T;
   const double sS = h->bf16 ? 2.0 : 4.0;
-  if (hbm_bytes) *hbm_bytes = 28.0 * N * V + 2.0 * sS * N * K + 8.0 * V * K;
+  // 28 N V = M read in forward (4) + M, m, v read and written (24); with the first moment kept in bf16
+  // (staged bf16 mode) m costs 2 + 2 instead of 4 + 4 -> 24 N V ("if the moments are kept in BF16 ... state which")
+  if (hbm_bytes) *hbm_bytes = (h->staged ? 24.0 : 28.0) * N * V + 2.0 * sS * N * K + 8.0 * V * K;
   if (flops) *flops = 4.0 * N * V * K + (h->cfg.lambda_ct_islands > 0.f ? 4.0 * N * V * T : 0.0);
   return TGB200_OK;
 }

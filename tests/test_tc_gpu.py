@@ -179,3 +179,26 @@ def test_pair_kernel_with_regularisers_matches_oracle(precision, tol):
     out, hist = Mapper(M0=M0, precision=precision, device="cuda:0", **kw).train(3, print_each=None)
     assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in ho["total_loss"]]) < tol
     assert np.allclose(out.sum(axis=1), 1.0, atol=2e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_more_than_65535_voxels(precision):
+    """Sections with more spots than gridDim.y allows (Visium HD, Slide-seq, MERFISH): the per-voxel kernels put the
+    voxel index on gridDim.x.  Few cells / genes, neighbourhood + Getis-Ord terms on (CSR SpMM both ways)."""
+    from oracle.tangram_oracle import grid_graph, spatial_weights_from_graph
+    from tangram_b200 import Mapper
+    N, V, K = 6, 66_000, 5
+    rng = np.random.default_rng(4)
+    S = (rng.random((N, K)) + 0.1).astype(np.float32)
+    G = (rng.random((V, K)) + 0.1).astype(np.float32)
+    d = (G.sum(axis=1) / G.sum()).astype(np.float32)
+    conn, dist = grid_graph(V)
+    kw = dict(S=S, G=G, d=d, lambda_d=1.0, lambda_neighborhood_g1=0.5, lambda_getis_ord=0.3,
+              voxel_weights=spatial_weights_from_graph(conn, dist, True, True),
+              spatial_weights=spatial_weights_from_graph(conn, dist, False, True))
+    M0 = rng.standard_normal((N, V)).astype(np.float32)
+    oo, oh = OracleMapper(M0=M0, **kw).train(3, print_each=None)
+    out, hist = Mapper(M0=M0, device="cuda:0", precision=precision, **kw).train(3, print_each=None)
+    assert out.shape == (N, V) and np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < (2e-3 if precision == "bf16" else 2e-5)
+    assert rel_fro(out, oo) < (5e-2 if precision == "bf16" else 1e-4)

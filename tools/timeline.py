@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 eng.timeline(True)
 eng.run(3)
 rows = eng.timeline(False)
-last = {0: 0.0, 1: 0.0, 2: 0.0}
+last = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
 for nm, st, ms in rows:
     print(f"{ms:9.3f} ms  stream {st}  {nm:20s}  (+{ms - last[st]:.3f} since the previous launch on this stream)")
     last[st] = ms
