@@ -51,20 +51,34 @@ def is_current():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/tangram_b200.cu -> libtangram_b200.so (no-op when up to date)."""
+    """Compile csrc/tangram_b200.cu -> libtangram_b200.so (no-op when up to date).  Safe when several processes (the ranks of a
+    torchrun launch) find a stale library at the same time: one builds under a file lock into a temporary file that is
+    renamed into place, the others wait and then see the fresh stamp."""
     if not force and is_current():
         return LIB
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build tangram_b200's CUDA library")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "tangram_b200.cu"), "-ldl"]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    with open(STAMP, "w") as f:
-        f.write(_digest())
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():        # another process built it while we waited
+                return LIB
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "tangram_b200.cu"), "-ldl"]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP, "w") as f:
+                f.write(_digest())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB

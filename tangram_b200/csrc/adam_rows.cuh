@@ -181,6 +181,55 @@ k_adam_rows(const AdamRowsArgs p) {
   }
 }
 
+// ---- parity mode (bf16x3): the same streaming pass in the reference's arithmetic ---------------------------------------------
+// IEEE expf / div / sqrt, torch's single-tensor Adam op order (adam_update), P from the row-pass statistics (softmax_prob) --
+// element for element what the fused epilogue of round 1 (TcEpiAdam, exact path) computed, now fed by the fp32 dP the
+// store-only contraction left in HBM.  16 B/element in (M, m, v, dP), 12 B/element out.
+struct AdamRowsExactArgs {
+  float* M; float* m; float* v;          // [rows][ld]
+  const float* dp;                       // [rows][ld]
+  const RowStat* stats; const float* rdot;
+  int ld, V, row0, row1;
+  float lam_r, lam_l1, lam_l2;
+  AdamScalars a;
+};
+
+__global__ void __launch_bounds__(256)
+k_adam_rows_exact(const AdamRowsExactArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int row = p.row0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.row1) return;
+  const RowStat st = p.stats[row];
+  const float r = p.rdot[row];
+  const size_t base = (size_t)row * p.ld;
+  float* Mr = p.M + base; float* mr = p.m + base; float* vr = p.v + base;
+  const float* dr = p.dp + base;
+  for (int c = lane * 8; c < p.V; c += 256) {        // groups entirely in the padding are never touched
+    float x[8], m[8], v[8], d[8];
+    ldg256f(Mr + c, x); ldg256f(mr + c, m); ldg256f(vr + c, v); ldg256f(dr + c, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (c + e < p.V) {
+        const float pr = softmax_prob(x[e], st);
+        float g = d[e] - r;
+        if (p.lam_r != 0.f) g -= p.lam_r * (((x[e] - st.mx) - st.log_z) - st.h);
+        g *= pr;
+        if (p.lam_l1 != 0.f) g += p.lam_l1 * (float)((x[e] > 0.f) - (x[e] < 0.f));
+        if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x[e];
+        x[e] = adam_update(x[e], g, m[e], v[e], p.a);
+      }
+    }
+    stg256f(Mr + c, x); stg256f(mr + c, m); stg256f(vr + c, v);
+  }
+}
+
+static inline int adam_rows_exact_launch(const AdamRowsExactArgs& a, cudaStream_t s) {
+  const int rows = a.row1 - a.row0;
+  if (rows <= 0) return 0;
+  k_adam_rows_exact<<<(unsigned)ceil_div(rows, 8), 256, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 static inline int adam_rows_launch(const AdamRowsArgs& a, cudaStream_t s) {
   const int rows = a.row1 - a.row0;
   if (rows <= 0) return 0;

@@ -2,10 +2,10 @@
 // TMA (128B swizzle), tcgen05.mma issued by one elected thread, fp32 accumulators in TMEM,
 // tcgen05.ld back to registers for the fused epilogues.
 //
-//   forward   Y_ext[z] = P[z]^T S_ext[z]        A = P  (MN-major), B = S_ext (MN-major), split over cells
-//   row-dot   r_i = <S_ext_i, (P dY_ext)_i>     A = P  (K-major),  B = dY_ext (MN-major), split over voxels
-//   backward  dP = S_ext dY_ext^T  -> softmax-Jacobian + Adam in the epilogue (A, B K-major); from 2048 cells up
-//             on CTA pairs (k_gemm_tc_pair: tcgen05 cta_group::2, 256-row tiles, half of B staged per CTA)
+//   forward   Y_ext[z] = P[z]^T S_ext[z]        A = P  (MN-major), B = S_ext (MN-major), split over cells / cell chunks
+//   backward  dP = S_ext dY_ext^T  -> stored (bf16 centred / fp32) + row-dot partials in the epilogue (A, B K-major);
+//             from 2048 cells up on CTA pairs (k_gemm_tc_pair: tcgen05 cta_group::2, 256-row tiles, half of B per CTA).
+//             The update itself is a streaming kernel (adam_rows.cuh).
 //
 // Persistent, warp-specialised kernel: one CTA per SM loops over output tiles.
 //   warp 0      TMA producer: keeps the operand ring full across tile boundaries
@@ -48,14 +48,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -65,24 +57,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kPolicyEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
-#ifndef TGB_EPI_LD_POLICY
-#define TGB_EPI_LD_POLICY kPolicyEvictFirst   // optimizer state is touched once per step
-#endif
-#ifndef TGB_EPI_ST_POLICY
-#define TGB_EPI_ST_POLICY kPolicyEvictFirst
-#endif
 // one full 32-byte sector per instruction (sm_100+: STG.256) -- 16-byte stores from a row-per-thread layout are partial-sector
 // writes, which cost L2 fill reads from DRAM
 __device__ __forceinline__ void stg256(void* dst, const uint32_t* w) {
   asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
                "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-}
-template <int WORDS>
-__device__ __forceinline__ void store_row_words(void* dst, const uint32_t (&w)[WORDS]) {
-  static_assert(WORDS % 4 == 0, "16-byte multiples");
-#pragma unroll
-  for (int u = 0; u < WORDS / 8; ++u) stg256(reinterpret_cast<uint8_t*>(dst) + 32 * u, &w[8 * u]);
-  if (WORDS % 8) reinterpret_cast<uint4*>(dst)[WORDS / 4 - 1] = make_uint4(w[WORDS - 4], w[WORDS - 3], w[WORDS - 2], w[WORDS - 1]);
 }
 // one full 32-byte sector per thread, read-only path (sm_100+: LDG.256)
 __device__ __forceinline__ void ldg256(const void* src, uint32_t (&w)[8]) {
@@ -94,35 +73,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -159,18 +109,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
 
 // ---- descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
@@ -212,37 +150,10 @@ struct OperandTile {
   }
 };
 
-// Optional phase timing of the backward epilogue (build with -DTGB_EPI_TIMING): lane 0 of every epilogue
-// warp accumulates clock64() deltas per phase into g_epi_timing[phase] (atomicAdd at kernel end).
-#ifdef TGB_EPI_TIMING
-__device__ unsigned long long g_epi_timing[8];
-#define TGB_T0() long long t__ = clock64()
-#define TGB_TICK(acc) do { long long n__ = clock64(); acc += n__ - t__; t__ = n__; } while (0)
-#else
-#define TGB_T0() do {} while (0)
-#define TGB_TICK(acc) do {} while (0)
-#endif
-
 // ---- epilogues ------------------------------------------------------------------------------
 // Each epilogue warp owns TMEM lanes [32q, 32q+32) = output rows m0+32q.. of the tile.
 // run() is called once per warp after the accumulator is complete; `scratch` is the (now idle)
 // operand ring, 1024-byte aligned, at least 32 KB.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // Coordinates of the work item an epilogue warp is draining.
 // Work item w -> (row tile m, column tile n).  Row tiles are taken in groups of `group_m`; inside a group the order is
 // column-major (all rows of the group for column 0, then column 1, ...).  The CTAs running at the same time then cover
@@ -262,22 +173,13 @@ struct TileCoord {
   int split;         // k-split index
 };
 
-// What the kernel hands to an epilogue that stages global data through shared memory with TMA.
-struct EpiCtx {
-  const CUtensorMap* map[3];   // state arrays (M, m, v) as fp32 2D tensors, box 32 x 32, 128B swizzle
-  uint32_t staging;            // shared-memory staging area (1024-byte aligned)
-  uint32_t bars;               // 16 mbarriers: [group 0..3][buffer 0..3]
-  uint32_t uses;               // bit b = phase parity of this thread's staging buffer b
-};
-
 struct TcEpiStore {
   float* C; int ldc; size_t split_stride; int M;
-  static constexpr int kStagingBytes = 0;
   template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, EpiCtx&) const {}
+  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int) const {}
   __device__ __forceinline__ void finish(int, int, int) const {}
   template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, EpiCtx&) const {
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t) const {
     static_assert(NW == 4, "one warp per TMEM lane quarter");
     const int row = t.m0 + q * 32 + lane;
 #pragma unroll 1
@@ -294,50 +196,6 @@ struct TcEpiStore {
   }
 };
 
-struct TcEpiRowDot {
-  const __nv_bfloat16* S; int lds; float* rpart; int M;
-  const float* Sf;       // parity mode: dot against the fp32 S_ext instead of its bf16 copy
-  static constexpr int kStagingBytes = 0;
-  template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord&, int, int, int, EpiCtx&) const {}
-  __device__ __forceinline__ void finish(int, int, int) const {}
-  template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int, int lane, const TileCoord& t, EpiCtx&) const {
-    static_assert(NW == 4, "one warp per TMEM lane quarter");
-    const int row = t.m0 + q * 32 + lane;
-    float acc = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      const int col = t.n0 + c;
-      if (row < M && col < lds && Sf != nullptr) {
-        const float4* src = reinterpret_cast<const float4*>(Sf + (size_t)row * lds + col);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float4 u = src[h];
-          acc = fmaf(v[4 * h + 0], u.x, acc); acc = fmaf(v[4 * h + 1], u.y, acc);
-          acc = fmaf(v[4 * h + 2], u.z, acc); acc = fmaf(v[4 * h + 3], u.w, acc);
-        }
-      } else if (row < M && col < lds) {
-        const uint4* src = reinterpret_cast<const uint4*>(S + (size_t)row * lds + col);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint4 u = src[h];
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-            acc = fmaf(v[h * 8 + 2 * e], __low2float(b), acc);
-            acc = fmaf(v[h * 8 + 2 * e + 1], __high2float(b), acc);
-          }
-        }
-      }
-    }
-    if (row < M) rpart[((size_t)t.split * t.tiles_n + t.tile_n) * M + row] = acc;
-  }
-};
-
 // Store-only backward epilogue (bf16 throughput mode, "staged" backward): dP = S_ext dY_ext^T leaves the kernel as
 // bf16, centred per row on the previous iteration's row-dot (dq_ij = bf16(dP_ij - c_i): the softmax-Jacobian only sees
 // dP_ij - r_i, so the bf16 rounding is relative to the deviation from the row mean, not to dP itself), and the same
@@ -349,11 +207,10 @@ struct TcEpiDpStore {
   const float* center;                                    // c_i (per row)
   float* rpart;                                           // [tiles_n * (NW / 4)][M]
   int M;
-  static constexpr int kStagingBytes = 0;
   // NW = 4: one warp per TMEM lane quarter takes all BN columns; NW = 8: two warps, BN / 2 columns each.  Four warps keep
   // the CTA small (192 threads) so that two CTAs of the streaming Adam kernel fit next to it on the SM.
   template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx&) const {
+  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane) const {
     static_assert(NW == 4 || NW == 8, "one or two warps per TMEM lane quarter");
     constexpr int W = BN / (NW / 4);
     const int row = t.m0 + q * 32 + lane, col = t.n0 + (ew >> 2) * W;
@@ -366,7 +223,7 @@ struct TcEpiDpStore {
   }
   __device__ __forceinline__ void finish(int, int, int) const {}
   template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx&) const {
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t) const {
     constexpr int PARTS = NW / 4, W = BN / PARTS, NCH = W / 16;
     const int part = ew >> 2;
     const int row = t.m0 + q * 32 + lane;
@@ -401,33 +258,74 @@ struct TcEpiDpStore {
   }
 };
 
+// The same store-only backward for the parity mode (bf16x3): dP leaves the kernel in fp32 (nothing to centre) and the
+// row-dot partials use P reconstructed from its three bf16 planes (hi + mid + lo = the fp32 value the row pass computed).
+struct TcEpiDpStoreF32 {
+  float* dp; int ld;                       // [rows][ld] fp32
+  const __nv_bfloat16* P3; size_t plane;   // three planes of [rows][ld] bf16
+  float* rpart;                            // [tiles_n * (NW / 4)][M]
+  int M;
+  template <int BN, int NW>
+  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane) const {
+    static_assert(NW == 4 || NW == 8, "one or two warps per TMEM lane quarter");
+    constexpr int W = BN / (NW / 4);
+    const int row = t.m0 + q * 32 + lane, col = t.n0 + (ew >> 2) * W;
+    if (row < M) {
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const __nv_bfloat16* src = P3 + pl * plane + (size_t)row * ld + col;
+#pragma unroll
+        for (int b = 0; b < W; b += 64)
+          if (col + b < ld) prefetch_l2(src + b);
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(int, int, int) const {}
+  template <int BN, int NW>
+  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t) const {
+    constexpr int PARTS = NW / 4, W = BN / PARTS, NCH = W / 16;
+    const int part = ew >> 2;
+    const int row = t.m0 + q * 32 + lane;
+    const int cbase = t.n0 + part * W;
+    const bool live = row < M;
+    const __nv_bfloat16* prow = P3 + (size_t)row * ld;
+    float* drow = dp + (size_t)row * ld;
+    float racc = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < NCH; ++i) {
+      const int col0 = cbase + i * 16;
+      uint32_t ph[8], pm[8], pl[8];
+      if (live && col0 < ld) { ldg256(prow + col0, ph); ldg256(prow + plane + col0, pm); ldg256(prow + 2 * plane + col0, pl); }
+      float v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), v);
+      if (live && col0 < ld) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[e]);
+          const __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&pm[e]);
+          const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&pl[e]);
+          const float p0 = (__low2float(l2) + __low2float(m2)) + __low2float(h2);
+          const float p1 = (__high2float(l2) + __high2float(m2)) + __high2float(h2);
+          racc = fmaf(p0, v[2 * e], racc);
+          racc = fmaf(p1, v[2 * e + 1], racc);
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(v[e]);
+        stg256(drow + col0, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(v[8 + e]);
+        stg256(drow + col0 + 8, w);
+      }
+    }
+    if (live) rpart[((size_t)t.tile_n * PARTS + part) * M + row] = racc;
+  }
+};
+
 // Per-row constants of the backward epilogue: lse = exact log-sum-exp of the row (P_ij = exp(M_ij - lse)),
 // r = row-dot, h = sum_j P log P (entropy term only).
 struct __align__(16) RowConst { float lse, r, h, pad; };
 
-struct TcAdamArgs {
-  float* Mp; float* mp; float* vp; int ld; int V;
-  const RowConst* rowc;
-  float lam_r, lam_l1, lam_l2;
-  AdamScalars a;
-  // parity mode (bf16x3): IEEE math in the reference's op order, P from the row-pass statistics
-  const RowStat* stats;   // non-null selects the exact epilogue
-  const float* rdot;
-  // next iteration's forward operand and its per-row partial sums (see k_row_norm)
-  __nv_bfloat16* Pt;      // N x ld, Pt_ij = exp(Mnew_ij - lse_i)
-  float* zpart;           // [n_col_parts][N]
-  float* pxpart;          // or null
-  float* l1part;          // or null (then l2part is null too)
-  float* l2part;
-};
-
-// The three N x V state arrays are the HBM-bound part of the whole iteration (24 B/element), so the
-// epilogue is built around bytes in flight and full-line transactions: the two warps that share a
-// TMEM lane quarter form a group that stages 32-row x 32-column sub-tiles of M, m, v through shared
-// memory with TMA -- bulk tensor loads (128 contiguous bytes per row, 128B-swizzled so that one
-// thread per row reads and writes conflict-free) two sub-tiles deep, in-place update with one thread
-// per row (matching the TMEM accumulator layout), bulk tensor stores back.  No LSU traffic for the
-// state at all; the only per-thread global access is the bf16 P row for the next forward pass.
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -439,281 +337,6 @@ __device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
-#ifndef TGB_EPI_SW
-#define TGB_EPI_SW 32
-#endif
-#ifndef TGB_EPI_NBUF
-#define TGB_EPI_NBUF 1
-#endif
-#ifndef TGB_EPI_L2_AHEAD
-#define TGB_EPI_L2_AHEAD 1      // sub-tiles prefetched into L2 ahead of the staged ones
-#endif
-struct TcEpiAdam {
-  TcAdamArgs p; int M;
-  static constexpr int SW = TGB_EPI_SW;                    // staged sub-tile width (two warps): 32 or 16 columns
-  static constexpr int CW = SW / 2;                        // columns per warp per staged sub-tile
-  static constexpr int VPW = CW / 4;                       // float4 per warp-row per array
-  static constexpr int kArrayBytes = 32 * SW * 4;          // 32 rows x (128 | 64) B
-  static constexpr int kBufBytes = 3 * kArrayBytes;        // M, m, v
-  static constexpr int NBUF = TGB_EPI_NBUF;                // staging depth per lane quarter
-  static constexpr int kGroupBytes = NBUF * kBufBytes;
-  static constexpr int kStagingBytes = 4 * kGroupBytes;    // 4 lane quarters
-  // TMA SWIZZLE_128B (128-byte rows): 16-byte chunk jj of row r lives at chunk position jj ^ (r & 7);
-  // TMA SWIZZLE_64B (64-byte rows): at jj ^ ((r >> 1) & 3).  Either way one thread per row is conflict free.
-  static __device__ __forceinline__ uint32_t swz(int r, int jj) {
-    return SW == 32 ? (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4)) : (uint32_t)(r * 64 + ((jj ^ ((r >> 1) & 3)) << 4));
-  }
-
-  // bf16-mode arithmetic: approximate MUFU ops (ex2, sqrt, rcp), ~2 ulp -- far below bf16 operand noise
-  __device__ __forceinline__ float one(float x, float dp, float& m, float& v, const RowConst& rc, float lse_l2e) const {
-    const float pr = fast_ex2(fmaf(x, 1.4426950408889634f, -lse_l2e));
-    float g = dp - rc.r;
-    if (p.lam_r != 0.f) g -= p.lam_r * ((x - rc.lse) - rc.h);
-    g *= pr;
-    if (p.lam_l1 != 0.f) g += p.lam_l1 * (float)((x > 0.f) - (x < 0.f));
-    if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x;
-    m = fmaf(g - m, p.a.one_minus_beta1, m);
-    v = fmaf(p.a.one_minus_beta2 * g, g, v * p.a.beta2);
-    const float denom = fmaf(fast_sqrt(v), p.a.inv_bc2_sqrt, p.a.eps);
-    return fmaf(-p.a.step_size * m, fast_rcp(denom), x);
-  }
-  // Pt for the next forward pass + this thread's (= this row's) partial sums
-  __device__ __forceinline__ float next_p(float xn, float lse_l2e, float& zs, float& pxs, float& l1s, float& l2s) const {
-    const float pt = fast_ex2(fmaf(xn, 1.4426950408889634f, -lse_l2e));
-    zs += pt;
-    if (p.pxpart) pxs = fmaf(pt, xn, pxs);
-    if (p.l1part) { l1s += fabsf(xn); l2s = fmaf(xn, xn, l2s); }
-    return pt;
-  }
-  // Configuration measured on B200 at 100k x 10k x 2k (tools/mainloop_only.py, ms per backward launch):
-//   BN=128 ring 4x32KB staging 2-deep: 7.02   BN=128 5x32KB 1-deep: 6.79   BN=256 3x48KB 1-deep: 6.62
-//   BN=256 3x48KB 1-deep + L2 prefetch 1 ahead: 6.36 (chosen)   2 ahead: 6.87   BN=256 2x48KB 2-deep: 7.58
-// The L2->SM operand stream (A is re-read per column tile) competes with 26 B/element of state traffic,
-// so the wider tile (25% fewer operand bytes) and a deeper ring beat a deeper staging pipeline.
-//   CTA pairs (k_gemm_tc_pair, 256x256 per pair, 4x32KB ring): 1-deep 5.75-5.94   2-deep 5.83-5.89   3x32KB ring 2-deep: 6.50
-  // leader lane of a group: three bulk tensor loads of sub-tile `c` into staging buffer `b`
-  __device__ __forceinline__ void issue_loads(const EpiCtx& cx, int g, int b, int row0, int col) const {
-    const uint32_t bar = cx.bars + (uint32_t)(g * 4 + b) * 8u;
-    const uint32_t dst = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
-    mbar_expect_tx_u32(bar, kBufBytes);
-    tma_load_2d_u32(cx.map[0], bar, dst, col, row0, TGB_EPI_LD_POLICY);
-    tma_load_2d_u32(cx.map[1], bar, dst + kArrayBytes, col, row0, TGB_EPI_LD_POLICY);
-    tma_load_2d_u32(cx.map[2], bar, dst + 2 * kArrayBytes, col, row0, TGB_EPI_LD_POLICY);
-  }
-  // DRAM -> L2 prefetch of a sub-tile a short, fixed distance ahead of its bulk load (a few microseconds:
-  // long enough to hide DRAM latency, short enough that the lines are still in L2 when the load arrives)
-  __device__ __forceinline__ void prefetch_l2(const EpiCtx& cx, int row0, int col) const {
-    if (col < p.V) {
-      tma_prefetch_l2_2d(cx.map[0], col, row0);
-      tma_prefetch_l2_2d(cx.map[1], col, row0);
-      tma_prefetch_l2_2d(cx.map[2], col, row0);
-    }
-  }
-  __device__ __forceinline__ void issue_stores(const EpiCtx& cx, int g, int b, int row0, int col) const {
-    const uint32_t src = cx.staging + (uint32_t)(g * kGroupBytes + b * kBufBytes);
-    tma_store_2d(cx.map[0], src, col, row0, TGB_EPI_ST_POLICY);
-    tma_store_2d(cx.map[1], src + kArrayBytes, col, row0, TGB_EPI_ST_POLICY);
-    tma_store_2d(cx.map[2], src + 2 * kArrayBytes, col, row0, TGB_EPI_ST_POLICY);
-    bulk_commit();
-  }
-  // Issued before the wait on the accumulator: the first two sub-tiles are already in flight when the
-  // MMAs of this tile retire.  (The leader drained its bulk stores at the end of the previous tile.)
-  template <int BN, int NW>
-  __device__ __forceinline__ void prologue(const TileCoord& t, int q, int ew, int lane, EpiCtx& cx) const {
-    static_assert(NW == 8, "two warps per TMEM lane quarter");
-    if (ew < 4 && lane == 0) {
-#pragma unroll
-      for (int b = 0; b < NBUF; ++b) issue_loads(cx, q, b, t.m0 + q * 32, t.n0 + b * SW);
-      for (int k = 0; k < TGB_EPI_L2_AHEAD; ++k) prefetch_l2(cx, t.m0 + q * 32, t.n0 + (NBUF + k) * SW);
-    }
-  }
-  __device__ __forceinline__ void finish(int ew, int lane, int) const {
-    if (ew < 4 && lane == 0) bulk_wait0();     // all bulk stores of this CTA have landed before exit
-  }
-  // Two adjacent elements of one row through the whole update (default loss: no entropy / L1 / L2):
-  // 13 packed FMA-pipe instructions + 8 MUFU for the pair.
-  struct PairConsts { f32x2 l2e, nlse, nr, omb1, omb2, b2, ibc, eps, nstep; };
-  __device__ __forceinline__ void pair(float& x0, float& x1, float dp0, float dp1, float& m0, float& m1, float& v0,
-                                       float& v1, const PairConsts& k, float& p0, float& p1) const {
-    f32x2 x = pk2(x0, x1), m = pk2(m0, m1), v = pk2(v0, v1);
-    f32x2 t = fma2(x, k.l2e, k.nlse);
-    float e0, e1;
-    upk2(t, e0, e1);
-    f32x2 g = mul2(add2(pk2(dp0, dp1), k.nr), pk2(fast_ex2(e0), fast_ex2(e1)));
-    m = fma2(add2(g, m ^ 0x8000000080000000ull), k.omb1, m);          // m + (g - m)(1-b1)
-    v = fma2(mul2(k.omb2, g), g, mul2(v, k.b2));
-    float s0, s1;
-    upk2(v, s0, s1);
-    f32x2 den = fma2(pk2(fast_sqrt(s0), fast_sqrt(s1)), k.ibc, k.eps);
-    float d0, d1;
-    upk2(den, d0, d1);
-    x = fma2(mul2(k.nstep, m), pk2(fast_rcp(d0), fast_rcp(d1)), x);
-    t = fma2(x, k.l2e, k.nlse);
-    upk2(t, e0, e1);
-    p0 = fast_ex2(e0); p1 = fast_ex2(e1);
-    upk2(x, x0, x1); upk2(m, m0, m1); upk2(v, v0, v1);
-  }
-  __device__ __forceinline__ void update_chunk_fast(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[CW],
-                                                    const RowConst& rc, float lse_l2e, float& zs) const {
-    PairConsts k;
-    k.l2e = pk2(1.4426950408889634f, 1.4426950408889634f); k.nlse = pk2(-lse_l2e, -lse_l2e); k.nr = pk2(-rc.r, -rc.r);
-    k.omb1 = pk2(p.a.one_minus_beta1, p.a.one_minus_beta1); k.omb2 = pk2(p.a.one_minus_beta2, p.a.one_minus_beta2);
-    k.b2 = pk2(p.a.beta2, p.a.beta2); k.ibc = pk2(p.a.inv_bc2_sqrt, p.a.inv_bc2_sqrt); k.eps = pk2(p.a.eps, p.a.eps);
-    k.nstep = pk2(-p.a.step_size, -p.a.step_size);
-    uint32_t pkd[2 * VPW];
-#pragma unroll
-    for (int j = 0; j < VPW; ++j) {
-      const uint32_t sp = buf + swz(lane, jbase + j);
-      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
-      float p0, p1, p2, p3;
-      pair(x.x, x.y, acc[4 * j + 0], acc[4 * j + 1], m.x, m.y, v.x, v.y, k, p0, p1);
-      pair(x.z, x.w, acc[4 * j + 2], acc[4 * j + 3], m.z, m.w, v.z, v.w, k, p2, p3);
-      zs += (p0 + p1) + (p2 + p3);
-      sts128(sp, x);
-      sts128(sp + kArrayBytes, m);
-      sts128(sp + 2 * kArrayBytes, v);
-      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-      pkd[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
-      pkd[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
-    }
-#ifndef TGB_SKIP_PWRITE
-    store_row_words(p.Pt + (size_t)row * p.ld + col0, pkd);
-#else
-    if (zs == -1.2345f) *reinterpret_cast<uint4*>(p.Pt) = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
-#endif
-  }
-  // parity-mode update of one 16-column sub-tile: same arithmetic as the FFMA path's EpiAdam (gemm_simt.cuh)
-  __device__ __forceinline__ float one_exact(float x, float dp, float& m, float& v, const RowStat& st, float r) const {
-    const float pr = softmax_prob(x, st);
-    float g = dp - r;
-    if (p.lam_r != 0.f) g -= p.lam_r * (((x - st.mx) - st.log_z) - st.h);
-    g *= pr;
-    if (p.lam_l1 != 0.f) g += p.lam_l1 * (float)((x > 0.f) - (x < 0.f));
-    if (p.lam_l2 != 0.f) g += 2.f * p.lam_l2 * x;
-    return adam_update(x, g, m, v, p.a);
-  }
-  __device__ __forceinline__ void update_chunk_exact(uint32_t buf, int jbase, int lane, int col0, const float (&acc)[CW],
-                                                     const RowStat& st, float r) const {
-#pragma unroll
-    for (int j = 0; j < VPW; ++j) {
-      const uint32_t sp = buf + swz(lane, jbase + j);
-      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
-      const int col = col0 + 4 * j;
-      if (col + 0 < p.V) x.x = one_exact(x.x, acc[4 * j + 0], m.x, v.x, st, r);
-      if (col + 1 < p.V) x.y = one_exact(x.y, acc[4 * j + 1], m.y, v.y, st, r);
-      if (col + 2 < p.V) x.z = one_exact(x.z, acc[4 * j + 2], m.z, v.z, st, r);
-      if (col + 3 < p.V) x.w = one_exact(x.w, acc[4 * j + 3], m.w, v.w, st, r);
-      sts128(sp, x);
-      sts128(sp + kArrayBytes, m);
-      sts128(sp + 2 * kArrayBytes, v);
-    }
-  }
-  // one 16-column sub-tile, thread = row.  GUARD=false: all 16 columns are real voxels.
-  template <bool GUARD>
-  __device__ __forceinline__ void update_chunk(uint32_t buf, int jbase, int lane, int row, int col0, const float (&acc)[CW],
-                                               const RowConst& rc, float lse_l2e, float& zs, float& pxs, float& l1s,
-                                               float& l2s) const {
-    uint32_t pk[2 * VPW];
-#pragma unroll
-    for (int j = 0; j < VPW; ++j) {
-      const uint32_t sp = buf + swz(lane, jbase + j);
-      float4 x = lds128(sp), m = lds128(sp + kArrayBytes), v = lds128(sp + 2 * kArrayBytes);
-      const int col = col0 + 4 * j;
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-      if (!GUARD || col + 0 < p.V) { x.x = one(x.x, acc[4 * j + 0], m.x, v.x, rc, lse_l2e); p0 = next_p(x.x, lse_l2e, zs, pxs, l1s, l2s); }
-      if (!GUARD || col + 1 < p.V) { x.y = one(x.y, acc[4 * j + 1], m.y, v.y, rc, lse_l2e); p1 = next_p(x.y, lse_l2e, zs, pxs, l1s, l2s); }
-      if (!GUARD || col + 2 < p.V) { x.z = one(x.z, acc[4 * j + 2], m.z, v.z, rc, lse_l2e); p2 = next_p(x.z, lse_l2e, zs, pxs, l1s, l2s); }
-      if (!GUARD || col + 3 < p.V) { x.w = one(x.w, acc[4 * j + 3], m.w, v.w, rc, lse_l2e); p3 = next_p(x.w, lse_l2e, zs, pxs, l1s, l2s); }
-      sts128(sp, x);
-      sts128(sp + kArrayBytes, m);
-      sts128(sp + 2 * kArrayBytes, v);
-      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-      pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
-      pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
-    }
-    // 16 bf16 = one 32-byte sector per row, written straight from the row-owning thread
-    store_row_words(p.Pt + (size_t)row * p.ld + col0, pk);
-  }
-  // ew = epilogue warp index; group = TMEM lane quarter q; part = ew / 4 picks the 16-column half of every
-  // 32-column staged sub-tile.
-  template <int BN, int NW>
-  __device__ __forceinline__ void run(uint32_t tmem_acc, int q, int ew, int lane, const TileCoord& t, EpiCtx& cx) const {
-    static_assert(NW == 8, "two warps per TMEM lane quarter");
-    constexpr int NCHUNK = BN / SW;
-    static_assert(NCHUNK >= NBUF && NBUF <= 4, "prologue prefetches NBUF sub-tiles");
-    const int part = ew >> 2;
-    const bool leader = (part == 0) && (lane == 0);
-    const int row0 = t.m0 + q * 32;
-    const int row = row0 + lane;
-    const bool exact = p.stats != nullptr;
-    RowConst rc = {0.f, 0.f, 0.f, 0.f};
-    RowStat st = {0.f, 1.f, 0.f, 0.f};
-    float rex = 0.f;
-    if (row < M) {
-      if (exact) { st = p.stats[row]; rex = p.rdot[row]; }
-      else rc = p.rowc[row];
-    }
-    const float lse_l2e = rc.lse * 1.4426950408889634f;
-    float zs = 0.f, pxs = 0.f, l1s = 0.f, l2s = 0.f;
-    const bool plain = p.lam_r == 0.f && p.lam_l1 == 0.f && p.lam_l2 == 0.f;   // default loss: packed fast path
-#ifdef TGB_EPI_TIMING
-    long long tw = 0, tc = 0, tb = 0, tp = 0;
-#endif
-    TGB_T0();
-#pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int b = c % NBUF;
-      const uint32_t buf = cx.staging + (uint32_t)(q * kGroupBytes + b * kBufBytes);
-      const int colg = t.n0 + c * SW;             // first column of the staged sub-tile
-      const int col0 = colg + part * CW;          // first column this warp updates
-      mbar_wait_u32(cx.bars + (uint32_t)(q * 4 + b) * 8u, (cx.uses >> b) & 1u);
-      cx.uses ^= (1u << b);                       // per-buffer phase parity
-      TGB_TICK(tw);
-      float acc[CW];
-      tmem_ld_cols(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 - t.n0), acc);
-      if (exact) {
-        if (row < M && col0 < p.V) update_chunk_exact(buf, part * VPW, lane, col0, acc, st, rex);
-      } else if (row < M && col0 < p.ld) {
-        if (col0 + CW <= p.V) {
-          if (plain) update_chunk_fast(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs);
-          else update_chunk<false>(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
-        } else {
-          update_chunk<true>(buf, part * VPW, lane, row, col0, acc, rc, lse_l2e, zs, pxs, l1s, l2s);
-        }
-      }
-      TGB_TICK(tc);
-      fence_proxy_async();                        // generic-proxy writes -> visible to the bulk store
-      named_bar_sync(1 + q, 64);                  // both warps of the group are done with this buffer
-      TGB_TICK(tb);
-      if (leader) {
-        issue_stores(cx, q, b, row0, colg);
-        if (c + NBUF < NCHUNK) {
-          bulk_wait_read0();                      // the store has read the buffer: refill it
-          issue_loads(cx, q, b, row0, colg + NBUF * SW);
-        }
-        if (TGB_EPI_L2_AHEAD > 0 && c + NBUF + TGB_EPI_L2_AHEAD < NCHUNK)
-          prefetch_l2(cx, row0, colg + (NBUF + TGB_EPI_L2_AHEAD) * SW);
-      }
-      TGB_TICK(tp);
-    }
-    if (leader) bulk_wait_read0();                // buffers reusable by the next tile's prologue
-#ifdef TGB_EPI_TIMING
-    if (lane == 1) {
-      atomicAdd(&g_epi_timing[0], (unsigned long long)tw); atomicAdd(&g_epi_timing[1], (unsigned long long)tc);
-      atomicAdd(&g_epi_timing[2], (unsigned long long)tb); atomicAdd(&g_epi_timing[3], (unsigned long long)tp);
-      atomicAdd(&g_epi_timing[4], 1ull);
-    }
-    if (leader) { atomicAdd(&g_epi_timing[6], (unsigned long long)tp); atomicAdd(&g_epi_timing[7], 1ull); }
-#endif
-    if (row < M && !exact) {
-      const size_t o = ((size_t)t.tile_n * 2 + part) * M + row;
-      p.zpart[o] = zs;
-      if (p.pxpart) p.pxpart[o] = pxs;
-      if (p.l1part) { p.l1part[o] = l1s; p.l2part[o] = l2s; }
-    }
-  }
-};
 
 // ---- split-precision operands -------------------------------------------------------------------
 // Parity mode on tensor cores ("bf16x3"): every fp32 operand value x is stored as three bf16 planes
@@ -731,8 +354,6 @@ __device__ __constant__ int kPairB[6] = {0, 2, 1, 0, 1, 0};
 template <bool A_KMAJOR, bool B_KMAJOR, int BN, int STAGES, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
-          const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
-          const __grid_constant__ CUtensorMap map_e2,
           int k_total, int k_per_split, int tiles_m, int tiles_n, int splits, int group_m, uint64_t policy_a,
           uint64_t policy_b, int tm_off, int k_off, const Epi epi) {
   using TileA = OperandTile<A_KMAJOR, TC_BM>;
@@ -748,7 +369,6 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
-  __shared__ __align__(8) uint64_t epi_bar[16];     // epilogue staging: [lane quarter][buffer]
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -761,9 +381,6 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
-#pragma unroll
-    for (int b = 0; b < 16; ++b) mbar_init(&epi_bar[b], 1);
-    if (Epi::kStagingBytes > 0) { tma_prefetch_desc(&map_e0); tma_prefetch_desc(&map_e1); tma_prefetch_desc(&map_e2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -835,11 +452,6 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
     // ===== epilogue warps: TMEM -> registers -> fused epilogue =====
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int ew = warp - 2;
-    EpiCtx cx;
-    cx.map[0] = &map_e0; cx.map[1] = &map_e1; cx.map[2] = &map_e2;
-    cx.staging = smem_u32(smem + STAGES * kStageBytes);
-    cx.bars = smem_u32(&epi_bar[0]);
-    cx.uses = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       TileCoord t;
@@ -851,18 +463,12 @@ k_gemm_tc(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps 
       t.m0 = (tm_off + tm_i) * TC_BM;
       const int b = it & 1;
 #ifndef TGB_SKIP_EPI
-      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
-#endif
-#ifdef TGB_EPI_TIMING
-      long long tq0 = clock64();
+      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane);
 #endif
       mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
-#ifdef TGB_EPI_TIMING
-      if (lane == 1 && Epi::kStagingBytes > 0) atomicAdd(&g_epi_timing[5], (unsigned long long)(clock64() - tq0));
-#endif
       tc_fence_after();
 #ifndef TGB_SKIP_EPI
-      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, cx);
+      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t);
 #endif
       tc_fence_before();
       __syncwarp();
@@ -928,9 +534,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // K-major A and B only (the backward contraction).  tiles_m counts 256-row pair tiles; grid = 2 x clusters.
 template <int BN, int STAGES, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs,
-               const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
-               const __grid_constant__ CUtensorMap map_e2, int k_total, int tiles_m, int tiles_n, int group_m,
+k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ TcMaps maps_b, int n_pairs, int k_total, int tiles_m, int tiles_n, int group_m,
                uint64_t policy_a, uint64_t policy_b, int tm_off, const Epi epi) {
   using TileA = OperandTile<true, TC_BM>;         // this CTA's 128 rows
   using TileB = OperandTile<true, BN / 2>;        // this CTA's half of the B tile
@@ -945,7 +549,6 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
-  __shared__ __align__(8) uint64_t epi_bar[16];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -961,9 +564,6 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
-#pragma unroll
-    for (int b = 0; b < 16; ++b) mbar_init(&epi_bar[b], 1);
-    if (Epi::kStagingBytes > 0) { tma_prefetch_desc(&map_e0); tma_prefetch_desc(&map_e1); tma_prefetch_desc(&map_e2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
@@ -1036,11 +636,6 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
     // ===== epilogue warps (both CTAs): each CTA owns 128 rows of the pair tile =====
     const int q = warp & 3;
     const int ew = warp - 2;
-    EpiCtx cx;
-    cx.map[0] = &map_e0; cx.map[1] = &map_e1; cx.map[2] = &map_e2;
-    cx.staging = smem_u32(smem + STAGES * kStageBytes);
-    cx.bars = smem_u32(&epi_bar[0]);
-    cx.uses = 0;
     const uint32_t tempty_remote = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     int it = 0;
     for (int w = cid; w < total; w += ncl, ++it) {
@@ -1053,12 +648,12 @@ k_gemm_tc_pair(const __grid_constant__ TcMaps maps_a, const __grid_constant__ Tc
       t.split = 0;
       const int b = it & 1;
 #ifndef TGB_SKIP_EPI
-      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane, cx);
+      epi.template prologue<BN, EPI_WARPS>(t, q, ew, lane);
 #endif
       mbar_wait(&tfull_bar[b], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
 #ifndef TGB_SKIP_EPI
-      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t, cx);
+      epi.template run<BN, EPI_WARPS>(tmem_base + (uint32_t)(b * BN), q, ew, lane, t);
 #endif
       tc_fence_before();
       __syncwarp();
@@ -1118,24 +713,6 @@ static inline int tc_make_map(TcContext& tc, CUtensorMap* map, const void* base,
   return 0;
 }
 
-static inline int tc_make_map_f32(TcContext& tc, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows,
-                                  uint64_t ld, uint32_t box_inner, uint32_t box_outer, char* err, size_t n) {
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 4};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = tc.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner * 4 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    snprintf(err, n, "cuTensorMapEncodeTiled(f32) failed (%d) cols=%llu rows=%llu ld=%llu", (int)r,
-             (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
-    return -2;
-  }
-  return 0;
-}
-
 // cudaFuncSetAttribute once per (handle, kernel): it is a driver call, not something to repeat on every launch
 template <class Kern>
 static inline int tc_set_smem(TcContext& tc, Kern kern, int bytes, char* err, size_t n) {
@@ -1157,28 +734,15 @@ static inline int tc_check_launch(const char* name, char* err, size_t n) {
 }
 
 constexpr int TC_FWD_BN = 256, TC_FWD_STAGES = 4;
-#ifndef TGB_BWD_STAGES
-#define TGB_BWD_STAGES 3
-#endif
-#ifndef TGB_BWD_POLICY_A
-#define TGB_BWD_POLICY_A kPolicyEvictNormal
-#endif
-#ifndef TGB_BWD_POLICY_B
-#define TGB_BWD_POLICY_B kPolicyEvictLast
-#endif
 #ifndef TGB_BWD_BN
 #define TGB_BWD_BN 256
 #endif
-constexpr int TC_BWD_BN = TGB_BWD_BN, TC_BWD_STAGES = TGB_BWD_STAGES, TC_BWD_EPI_WARPS = 8;
-constexpr int TC_RD_STAGES = 4;
+constexpr int TC_BWD_BN = TGB_BWD_BN;
 // CTA-pair backward kernel (cta_group::2): used from TC_PAIR_MIN_ROWS cells up (smaller problems don't fill 74 pairs)
 #ifndef TGB_BWD_PAIR
 #define TGB_BWD_PAIR 1
 #endif
-#ifndef TGB_PAIR_STAGES
-#define TGB_PAIR_STAGES 4
-#endif
-constexpr int TC_PAIR_STAGES = TGB_PAIR_STAGES, TC_PAIR_MIN_ROWS = 2048;
+constexpr int TC_PAIR_MIN_ROWS = 2048;
 // store-only backward (staged dP): no epilogue staging in shared memory, so the operand ring can be deeper
 #ifndef TGB_DP_STAGES
 #define TGB_DP_STAGES 6
@@ -1188,11 +752,7 @@ constexpr int TC_PAIR_STAGES = TGB_PAIR_STAGES, TC_PAIR_MIN_ROWS = 2048;
 #endif
 constexpr int TC_DP_STAGES = TGB_DP_STAGES, TC_DP_SINGLE_STAGES = 4, TC_DP_EPI_WARPS = TGB_DP_EPI_WARPS;
 static inline int tc_dp_row_parts(int V) { return (int)ceil_div(V, TC_BWD_BN) * (TC_DP_EPI_WARPS / 4); }
-// Row tiles per scheduling group of the backward kernel (tile_mn).  Measured at 100k x 10k x 2k, ms per launch:
-// 1: 5.75   4: 5.84   8: 5.86   16: 5.89   37: 7.03 -- many CTAs pulling the same B tile at once hot-spot L2 slices.
-#ifndef TGB_BWD_GROUP
-#define TGB_BWD_GROUP 1
-#endif
+// (tile_mn's row-tile groups stay at 1: more CTAs pulling the same B tile at once hot-spot L2 slices -- measured in round 1.)
 static inline int tc_splits(long long tiles, long long k_total, int min_k) {
   long long s = (2 * 148 + tiles - 1) / tiles;
   const long long max_s = (k_total + min_k - 1) / min_k;
@@ -1215,11 +775,6 @@ static inline int tc_splits_for_chain(long long k_total, int max_chain) {
 static inline int tc_forward_splits(int N, int V, int Ke) {
   return tc_splits((long long)ceil_div(V, TC_BM) * ceil_div(Ke, TC_FWD_BN), N, 512);
 }
-static inline int tc_rowdot_splits(int N, int V, int Ke) {
-  return tc_splits((long long)ceil_div(N, TC_BM) * ceil_div(Ke, TC_RDOT_BN), V, 1024);
-}
-// partial-sum arrays written by the backward epilogue: one per (voxel tile, column part)
-static inline int tc_bwd_col_parts(int V) { return (int)ceil_div(V, TC_BWD_BN) * (TC_BWD_EPI_WARPS / 4); }
 static inline int tc_kps(int k_total, int splits) {
   return (int)(round_up(ceil_div(k_total, splits), TC_BK));
 }
@@ -1241,7 +796,6 @@ static inline int tc_make_maps(TcContext& tc, TcMaps* maps, const __nv_bfloat16*
 // encodes each plan once (the buffers never move) instead of on every launch.
 struct TcPlan {
   TcMaps a, b;
-  CUtensorMap e[3];
   bool pair = false;        // b is encoded for the CTA-pair kernel (half-tile boxes)
   bool ready = false;
 };
@@ -1261,7 +815,7 @@ static inline int tc_forward_launch(TcContext& tc, const TcPlan& pl, int n_pairs
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], N, tc_kps(N, splits), tm, tn,
+  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, N, tc_kps(N, splits), tm, tn,
                                                                          splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, 0, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
@@ -1274,7 +828,7 @@ static inline int tc_forward_launch_rows(TcContext& tc, const TcPlan& pl, float*
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], row1, (int)round_up(row1 - row0, TC_BK), tm, tn,
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, 1, row1, (int)round_up(row1 - row0, TC_BK), tm, tn,
                                                                 1, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, row0, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
@@ -1285,26 +839,6 @@ static inline int tc_forward(TcContext& tc, const __nv_bfloat16* P, size_t p_pla
   TcPlan pl;
   if (tc_forward_plan(tc, pl, P, p_plane, Sx, s_plane, n_pairs > 1 ? 3 : 1, N, V, Ke, ld, err, n)) return -2;
   return tc_forward_launch(tc, pl, n_pairs, out, N, V, Ke, splits, s, err, n);
-}
-
-// rpart[(z * ntiles_n + tn)][i] = sum over the tile's genes of (P dY_ext)_ik S_ext_ik
-static inline int tc_rowdot_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* P, size_t p_plane, const __nv_bfloat16* dYb,
-                                 size_t dy_plane, int planes, int N, int V, int Ke, int ld, char* err, size_t n) {
-  if (tc_make_maps(tc, &pl.a, P, p_plane, planes, V, N, ld, 64, TC_BM, err, n)) return -2;   // A: K-major (contraction over voxels)
-  if (tc_make_maps(tc, &pl.b, dYb, dy_plane, planes, Ke, V, Ke, 64, 64, err, n)) return -2;  // B: MN-major (genes contiguous), rows = voxels
-  pl.ready = true;
-  return 0;
-}
-static inline int tc_rowdot_launch(TcContext& tc, const TcPlan& pl, int n_pairs, const __nv_bfloat16* Sxb, const float* Sxf,
-                                   float* rpart, int N, int V, int Ke, int splits, cudaStream_t s, char* err, size_t n) {
-  auto kern = k_gemm_tc<true, false, TC_RDOT_BN, TC_RD_STAGES, 4, TcEpiRowDot>;
-  const int smem = TC_RD_STAGES * (TC_BM + TC_RDOT_BN) * TC_BK * 2 + 1024;
-  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
-  TcEpiRowDot epi{Sxb, Ke, rpart, N, Sxf};
-  const int tm = (int)ceil_div(N, TC_BM), tn = (int)ceil_div(Ke, TC_RDOT_BN);
-  kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, pl.a.m[0], pl.a.m[0], pl.a.m[0], V, tc_kps(V, splits), tm, tn,
-                                                                         splits, 1, kPolicyEvictNormal, kPolicyEvictLast, 0, 0, epi);
-  return tc_check_launch("tc_gemm_rowdot", err, n);
 }
 
 // number of co-resident 2-CTA clusters of a pair kernel (persistent: never launch more), 0 = unavailable
@@ -1334,92 +868,47 @@ static inline cudaError_t tc_launch_pair(Kern pk, unsigned clusters, int threads
   return cudaLaunchKernelEx(&cfg, pk, args...);
 }
 
-// dP = S_ext dY_ext^T fused with the softmax-Jacobian and Adam (parity mode; the bf16 mode before the staged backward)
-static inline int tc_backward_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* Sxb, size_t s_plane, const __nv_bfloat16* dYb,
-                                   size_t dy_plane, int planes, const TcAdamArgs& a, int N, int V, int Ke, cudaStream_t s,
-                                   char* err, size_t n) {
-  if (tc_make_maps(tc, &pl.a, Sxb, s_plane, planes, Ke, N, Ke, 64, TC_BM, err, n)) return -2;     // A: K-major, rows = cells
-  // state arrays as fp32 2D tensors [N][V] (pitch ld): 32 x 32 boxes, 128B swizzle; stores clip at V / N
-  float* st[3] = {a.Mp, a.mp, a.vp};
-  for (int i = 0; i < 3; ++i)
-    if (tc_make_map_f32(tc, &pl.e[i], st[i], V, N, a.ld, TcEpiAdam::SW, 32, err, n)) return -2;
+// Staged backward: dq = bf16(S_ext dY_ext^T - centre) (bf16 mode) or dP in fp32 (bf16x3 mode, three operand planes, six
+// partial products) to HBM + row-dot partials; the update itself is a streaming kernel (adam_rows.cuh).  Rows [row0, row1)
+// only (row0 a multiple of 256): the host pipelines row chunks.
+template <class Epi>
+static inline int tc_dpstore_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* Sxb, size_t s_plane, const __nv_bfloat16* dYb,
+                                  size_t dy_plane, int planes, int N, int V, int Ke, cudaStream_t s, char* err, size_t n) {
+  if (tc_make_maps(tc, &pl.a, Sxb, s_plane, planes, Ke, N, Ke, 64, TC_BM, err, n)) return -2;
   pl.pair = false;
 #if TGB_BWD_PAIR
   if (N >= TC_PAIR_MIN_ROWS) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
-    const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
-    if (tc_set_smem(tc, pk, psmem, err, n)) return -2;
-    if (tc.pair_clusters < 0) tc.pair_clusters = tc_pair_clusters(tc, pk, 64 + 32 * TC_BWD_EPI_WARPS, psmem, s);
-    pl.pair = tc.pair_clusters > 0;   // 0: no room for 2-CTA clusters on this device (partitioned GPU) -> single-CTA kernel
-  }
-#endif
-  // B: K-major, rows = voxels; CTA pairs stage half of the B tile per CTA (box rows = BN / 2)
-  if (tc_make_maps(tc, &pl.b, dYb, dy_plane, planes, Ke, V, Ke, 64, pl.pair ? TC_BWD_BN / 2 : TC_BWD_BN, err, n)) return -2;
-  pl.ready = true;
-  return 0;
-}
-static inline int tc_backward_launch(TcContext& tc, const TcPlan& pl, int n_pairs, const TcAdamArgs& a, int N, int V, int Ke,
-                                     cudaStream_t s, char* err, size_t n) {
-  TcEpiAdam epi{a, N};
-  const int tn = (int)ceil_div(V, TC_BWD_BN);
-  if (pl.pair) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_PAIR_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
-    const int psmem = TC_PAIR_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
-    const int tmp = (int)ceil_div(N, 2 * TC_BM);
-    const long long pair_tiles = (long long)tmp * tn;
-    const unsigned clusters = (unsigned)(pair_tiles < tc.pair_clusters ? pair_tiles : tc.pair_clusters);
-    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * TC_BWD_EPI_WARPS, psmem, s, pl.a, pl.b, n_pairs, pl.e[0], pl.e[1], pl.e[2], Ke,
-                                   tmp, tn, TGB_BWD_GROUP, (uint64_t)TGB_BWD_POLICY_A, (uint64_t)TGB_BWD_POLICY_B, 0, epi);
-    if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_adam (pair): %s", cudaGetErrorString(e)); return -2; }
-    return tc_check_launch("tc_gemm_bwd_adam", err, n);
-  }
-  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_BWD_STAGES, TC_BWD_EPI_WARPS, TcEpiAdam>;
-  const int smem = TC_BWD_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + TcEpiAdam::kStagingBytes + 1024;
-  if (tc_set_smem(tc, kern, smem, err, n)) return -2;
-  const int tm = (int)ceil_div(N, TC_BM);
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_BWD_EPI_WARPS, smem, s>>>(pl.a, pl.b, n_pairs, pl.e[0], pl.e[1], pl.e[2], Ke, Ke, tm, tn, 1,
-                                                                              TGB_BWD_GROUP, TGB_BWD_POLICY_A, TGB_BWD_POLICY_B, 0, 0, epi);
-  return tc_check_launch("tc_gemm_bwd_adam", err, n);
-}
-
-// Staged backward (bf16 throughput mode): dq = bf16(S_ext dY_ext^T - centre) to HBM + row-dot partials; the update itself
-// is the streaming kernel k_adam_rows.  Rows [row0, row1) only (row0 a multiple of 256): the host pipelines row chunks.
-static inline int tc_dpstore_plan(TcContext& tc, TcPlan& pl, const __nv_bfloat16* Sxb, const __nv_bfloat16* dYb, int N, int V,
-                                  int Ke, cudaStream_t s, char* err, size_t n) {
-  if (tc_make_maps(tc, &pl.a, Sxb, 0, 1, Ke, N, Ke, 64, TC_BM, err, n)) return -2;
-  pl.pair = false;
-#if TGB_BWD_PAIR
-  if (N >= TC_PAIR_MIN_ROWS) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, Epi>;
     const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
     if (tc_set_smem(tc, pk, psmem, err, n)) return -2;
     if (tc.dp_clusters < 0) tc.dp_clusters = tc_pair_clusters(tc, pk, 64 + 32 * TC_DP_EPI_WARPS, psmem, s);
     pl.pair = tc.dp_clusters > 0;
   }
 #endif
-  if (tc_make_maps(tc, &pl.b, dYb, 0, 1, Ke, V, Ke, 64, pl.pair ? TC_BWD_BN / 2 : TC_BWD_BN, err, n)) return -2;
+  if (tc_make_maps(tc, &pl.b, dYb, dy_plane, planes, Ke, V, Ke, 64, pl.pair ? TC_BWD_BN / 2 : TC_BWD_BN, err, n)) return -2;
   pl.ready = true;
   return 0;
 }
-static inline int tc_dpstore_launch(TcContext& tc, const TcPlan& pl, const TcEpiDpStore& epi, int row0, int row1, int V, int Ke,
+template <class Epi>
+static inline int tc_dpstore_launch(TcContext& tc, const TcPlan& pl, int n_pairs, const Epi& epi, int row0, int row1, int V, int Ke,
                                     cudaStream_t s, char* err, size_t n) {
   const int tn = (int)ceil_div(V, TC_BWD_BN);
   if (pl.pair) {
-    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
+    auto pk = k_gemm_tc_pair<TC_BWD_BN, TC_DP_STAGES, TC_DP_EPI_WARPS, Epi>;
     const int psmem = TC_DP_STAGES * (TC_BM + TC_BWD_BN / 2) * TC_BK * 2 + 1024;
     const int tm0 = row0 / (2 * TC_BM), tmp = (int)ceil_div(row1, 2 * TC_BM) - tm0;
     const long long pair_tiles = (long long)tmp * tn;
     const unsigned clusters = (unsigned)(pair_tiles < tc.dp_clusters ? pair_tiles : tc.dp_clusters);
-    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * TC_DP_EPI_WARPS, psmem, s, pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, tmp, tn, 1,
+    cudaError_t e = tc_launch_pair(pk, clusters, 64 + 32 * TC_DP_EPI_WARPS, psmem, s, pl.a, pl.b, n_pairs, Ke, tmp, tn, 1,
                                    (uint64_t)kPolicyEvictNormal, (uint64_t)kPolicyEvictLast, tm0, epi);
     if (e != cudaSuccess) { snprintf(err, n, "launch tc_gemm_bwd_dp (pair): %s", cudaGetErrorString(e)); return -2; }
     return tc_check_launch("tc_gemm_bwd_dp", err, n);
   }
-  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_DP_SINGLE_STAGES, TC_DP_EPI_WARPS, TcEpiDpStore>;
+  auto kern = k_gemm_tc<true, true, TC_BWD_BN, TC_DP_SINGLE_STAGES, TC_DP_EPI_WARPS, Epi>;
   const int smem = TC_DP_SINGLE_STAGES * (TC_BM + TC_BWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
   const int tm0 = row0 / TC_BM, tm = (int)ceil_div(row1, TC_BM) - tm0;
-  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_DP_EPI_WARPS, smem, s>>>(pl.a, pl.b, 1, pl.a.m[0], pl.a.m[0], pl.a.m[0], Ke, Ke, tm, tn, 1, 1,
+  kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * TC_DP_EPI_WARPS, smem, s>>>(pl.a, pl.b, n_pairs, Ke, Ke, tm, tn, 1, 1,
                                                                                 kPolicyEvictNormal, kPolicyEvictLast, tm0, 0, epi);
   return tc_check_launch("tc_gemm_bwd_dp", err, n);
 }

@@ -704,19 +704,6 @@ __global__ void k_scale_rows_bf16(const float* __restrict__ Sx, const float* __r
   const float4 v = reinterpret_cast<const float4*>(Sx)[q];
   store_p4<__nv_bfloat16>(out + q * 4, v.x * s, v.y * s, v.z * s, v.w * s);
 }
-// rowc_i = (lseT_i, r_i = (sum of row-dot partials) / zt_i, h_i, 0)
-__global__ void k_rowdot_finalize_tc(const float* __restrict__ rpart, int nparts, int n_rows,
-                                     const float* __restrict__ lseT, const float* __restrict__ inv_zt,
-                                     const RowStat* __restrict__ stats, float* __restrict__ r, float4* __restrict__ rowc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += rpart[(size_t)p * n_rows + i];
-  s *= inv_zt[i];
-  r[i] = s;
-  rowc[i] = make_float4(lseT[i], s, stats[i].h, 0.f);
-}
-
 // Staged backward: the store-only contraction left partials of r'_i = sum_j Pt_ij (dP_ij - c_i); with P = Pt / zt:
 //   rowc_i = (lseT_i, r'_i / zt_i, h_i, 0) for the streaming Adam kernel,  r_i = c_i + r'_i / zt_i  (full row-dot),
 // and r_i becomes the centre of the next iteration's dq.  Rows [row0, row1).

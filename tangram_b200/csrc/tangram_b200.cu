@@ -102,7 +102,7 @@ struct tgb200_mapper {
   bool constrained = false, have_filter = false;
   DevBuf<float> Fl, mF, vF, fsig, Sf, fscal;
   int p_state = 0;              // 0: Pb invalid, 1: fresh from the row pass (normalised), 2: written by backward
-  int r_parts = 0, rd_splits = 1;
+  int r_parts = 0;
   // forward / loss
   int fwd_splits = 1;
   DevBuf<float> Ypart;          // splits x V x Ke (only when splits > 1)
@@ -124,7 +124,7 @@ struct tgb200_mapper {
   int64_t launches = 0;
   KernelTimer* timer = nullptr;
   TcContext tc;                 // driver entry points etc. for the tcgen05 path
-  TcPlan plan_fwd, plan_rd, plan_bwd, plan_dp;   // tensor maps of the contractions, encoded once (the buffers never move)
+  TcPlan plan_fwd, plan_dp;     // tensor maps of the two contractions, encoded once (the buffers never move)
   // staged backward (bf16 mode): store-only contraction -> bf16 dq = dP - centre in HBM -> streaming Adam kernel;
   // two contractions per iteration instead of three (no separate row-dot GEMM)
   bool staged = false;
@@ -133,6 +133,9 @@ struct tgb200_mapper {
                                 // exponential average with a 10-iteration memory: bf16 rounding noise does not accumulate, and
                                 // next to bf16 operands it is invisible in every parity metric; v stays fp32.
   DevBuf<float> rcenter;        // per row: last iteration's row-dot, the centre dq is stored relative to
+  // the same staging for the parity mode (bf16x3): dP in fp32, exact streaming update (no chunk pipeline)
+  bool staged_x3 = false;
+  DevBuf<float> dpf;            // N x ld
   // Pipelining of the staged backward over cell chunks (rows [chunk_row[c], chunk_row[c+1]), multiples of 256):
   //   hi (high-priority stream): forward(c) ... loss ... backward contraction(c)        -- tensor-core bound
   //   lo (low-priority stream):  row-dot finalize(c), streaming Adam(c)                 -- HBM bound
@@ -284,14 +287,13 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   const size_t nv = (size_t)h->N * h->ld, vk = (size_t)h->V * h->Ke;
   int st = TGB200_OK;
   auto A = [&](int s) { if (st == TGB200_OK) st = s; };
-  if (h->bf16) {
-    const char* bw = getenv("TGB200_BWD");          // "fused": the round-1 three-contraction pipeline (A/B measurements)
-    h->staged = !(bw && strcmp(bw, "fused") == 0);
-  }
+  h->staged = h->bf16;           // both tensor-core modes stage the backward contraction's result in HBM
+  h->staged_x3 = h->x3;
+  if (h->staged_x3) A(h->dpf.alloc(nv, false));
   A(h->M.alloc(nv)); A(h->v.alloc(nv));
   if (h->staged) A(h->mb.alloc(nv)); else A(h->m.alloc(nv));
   if (h->bf16) {
-    h->z_parts = h->staged ? 1 : tc_bwd_col_parts(h->V);
+    h->z_parts = 1;              // k_adam_rows: one warp per row, complete row sums
     A(h->Sxs.alloc((size_t)h->N * h->Ke)); A(h->lse0.alloc(h->N)); A(h->lse1.alloc(h->N)); A(h->inv_zt.alloc(h->N));
     A(h->zpart.alloc((size_t)h->z_parts * h->N));
     if (cfg->lambda_r != 0.f) A(h->pxpart.alloc((size_t)h->z_parts * h->N));
@@ -352,10 +354,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     A(h->Fl.alloc(h->N)); A(h->mF.alloc(h->N)); A(h->vF.alloc(h->N)); A(h->fsig.alloc(h->N));
     A(h->Sf.alloc((size_t)h->N * h->Ke)); A(h->fscal.alloc(4));
   }
-  h->rd_splits = h->tcm ? tc_rowdot_splits(h->N, h->V, h->Ke) : 1;
-  if (h->x3) { const int c = tc_splits_for_chain(h->V, 2048); if (c > h->rd_splits) h->rd_splits = c; }
-  h->r_parts = (int)ceil_div(h->Ke, h->tcm ? TC_RDOT_BN : SG_BN) * h->rd_splits;
-  if (h->staged) h->r_parts = tc_dp_row_parts(h->V);                   // TcEpiDpStore: one partial per (voxel tile, epilogue warp of a lane quarter)
+  h->r_parts = h->tcm ? tc_dp_row_parts(h->V) : (int)ceil_div(h->Ke, SG_BN);                   // TcEpiDpStore: one partial per (voxel tile, epilogue warp of a lane quarter)
   A(h->rpart.alloc((size_t)h->r_parts * h->N));
   A(h->ngc.alloc(h->Ke)); A(h->ngr.alloc(h->V));
   // voxel rows per CTA of the loss reductions: enough CTAs for small V, bounded partial arrays for large V
@@ -919,13 +918,14 @@ static int filter_update(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a)
 // Staged backward (bf16 mode): dq = bf16(S_ext dY_ext^T - centre) + row-dot partials from the store-only contraction,
 // then one streaming pass does softmax-Jacobian + Adam + the next forward's P.  (mapping_optimizer.py:395-396)
 static int backward_staged(tgb200_mapper* h, cudaStream_t s, cudaStream_t su, const AdamScalars& a) {
-  if (!h->plan_dp.ready) CKS(tc_dpstore_plan(h->tc, h->plan_dp, h->Sxb.p, h->dYb.p, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+  if (!h->plan_dp.ready)
+    CKS(tc_dpstore_plan<TcEpiDpStore>(h->tc, h->plan_dp, h->Sxb.p, 0, h->dYb.p, 0, 1, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
   const bool two_streams = su != s;
   const bool prefetch = two_streams && h->prefetch_next && h->nchunks > 1 && !h->constrained;
   for (int c = 0; c < h->nchunks; ++c) {
     const int r0 = h->nchunks > 1 ? h->chunk_row[c] : 0, r1 = h->nchunks > 1 ? h->chunk_row[c + 1] : h->N;
     TcEpiDpStore epi{h->dq.p, h->Pb.p, h->ld, h->rcenter.p, h->rpart.p, h->N};
-    CKS(tc_dpstore_launch(h->tc, h->plan_dp, epi, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    CKS(tc_dpstore_launch(h->tc, h->plan_dp, 1, epi, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_bwd_dp");
     if (two_streams) {
       CK(cudaEventRecord(h->ev_g[c], s));
@@ -959,6 +959,27 @@ static int backward_staged(tgb200_mapper* h, cudaStream_t s, cudaStream_t su, co
   return TGB200_OK;
 }
 
+// Staged backward of the parity mode (bf16x3): six partial products of S_ext dY_ext^T into fp32 dP + exact row-dot partials,
+// then the exact streaming update.  Two contractions per iteration instead of three here too.  (mapping_optimizer.py:395-396)
+static int backward_staged_x3(tgb200_mapper* h, cudaStream_t s, const AdamScalars& a) {
+  const size_t nkp = (size_t)h->N * h->Ke, vkp = (size_t)h->V * h->Ke, nvp = (size_t)h->N * h->ld;
+  if (!h->plan_dp.ready)
+    CKS(tc_dpstore_plan<TcEpiDpStoreF32>(h->tc, h->plan_dp, h->Sxb.p, nkp, h->dYb.p, vkp, 3, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+  TcEpiDpStoreF32 epi{h->dpf.p, h->ld, h->Pb.p, nvp, h->rpart.p, h->N};
+  // all six partial products: with only the three or four largest the one-step tests leave their 1e-5 band (measured
+  // 28.6 / 25.8 it/s at C3 instead of 21.2 -- not worth the parity-grade mode's point)
+  CKS(tc_dpstore_launch(h->tc, h->plan_dp, 6, epi, 0, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
+  mark(h, s, "tc_gemm_bwd_dp");
+  k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p, h->stats.p, nullptr);
+  LAUNCH_CHECK("rowdot_finalize");
+  if (h->constrained) CKS(filter_update(h, s, a));
+  AdamRowsExactArgs ar{h->M.p, h->m.p, h->v.p, h->dpf.p, h->stats.p, h->rdot.p, h->ld, h->V, 0, h->N,
+                       h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
+  if (adam_rows_exact_launch(ar, s)) return fail(TGB200_ERR_CUDA, "launch adam_rows_exact: %s", cudaGetErrorString(cudaGetLastError()));
+  mark(h, s, "adam_rows");
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   cudaStream_t caller = (cudaStream_t)stream;
@@ -974,60 +995,28 @@ extern "C" int tgb200_step_end(tgb200_mapper* h, float lr, void* stream) {
   if (h->pipelined && !h->serial) CK(cudaEventRecord(h->ev_loss, s));
 
   const AdamScalars a = adam_scalars(h->cfg, h->step + 1, lr);
-  const size_t nvp = (size_t)h->N * h->ld, vkp = (size_t)h->V * h->Ke, nkp = (size_t)h->N * h->Ke;
   if (h->staged) {
     CKS(backward_staged(h, s, update_stream(h, caller), a));
+  } else if (h->staged_x3) {
+    CKS(backward_staged_x3(h, s, a));
   } else {
-  if (h->tcm) {
-    if (!h->plan_rd.ready)
-      CKS(tc_rowdot_plan(h->tc, h->plan_rd, h->Pb.p, nvp, h->dYb.p, vkp, h->x3 ? 3 : 1, h->N, h->V, h->Ke, h->ld, g_err, sizeof(g_err)));
-    CKS(tc_rowdot_launch(h->tc, h->plan_rd, h->n_pairs, h->Sxb.p, h->x3 ? s_act(h) : nullptr, h->rpart.p, h->N, h->V, h->Ke, h->rd_splits,
-                         s, g_err, sizeof(g_err)));
-    mark(h, s, "tc_gemm_rowdot");
-  } else {
+    // fp32 cross-check mode: FFMA contractions (row-dot GEMM, then the backward GEMM with the fused exact epilogue)
     GemmArgs g;
     g.A = h->Pf.p; g.lda = h->ld; g.B = h->dY.p; g.ldb = h->Ke;
     g.M = h->N; g.N = h->Ke; g.K = h->V; g.k_per_split = (int)round_up(h->V, 16);
-    EpiRowDot epi{s_act(h), h->Ke, h->rpart.p};
-    dim3 grid((unsigned)ceil_div(h->Ke, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
-    k_gemm_simt<true, false, EpiRowDot><<<grid, SG_THREADS, 0, s>>>(g, epi);
+    EpiRowDot epi_r{s_act(h), h->Ke, h->rpart.p};
+    dim3 grid_r((unsigned)ceil_div(h->Ke, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
+    k_gemm_simt<true, false, EpiRowDot><<<grid_r, SG_THREADS, 0, s>>>(g, epi_r);
     LAUNCH_CHECK("simt_gemm_rowdot");
-  }
-  if (h->bf16) {
-    k_rowdot_finalize_tc<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->lseT, h->inv_zt.p, h->stats.p,
-                                                                        h->rdot.p, h->rowc.p);
-  } else {
     k_rowdot_finalize<<<(unsigned)ceil_div(h->N, 256), 256, 0, s>>>(h->rpart.p, h->r_parts, h->N, h->rdot.p, h->stats.p, nullptr);
-  }
-  LAUNCH_CHECK("rowdot_finalize");
-  if (h->constrained) CKS(filter_update(h, s, a));
-  if (h->tcm) {
-    TcAdamArgs ta{h->M.p, h->m.p, h->v.p, h->ld, h->V, nullptr, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a,
-                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (h->bf16) {
-      ta.rowc = reinterpret_cast<const RowConst*>(h->rowc.p);
-      ta.Pt = h->Pb.p; ta.zpart = h->zpart.p; ta.pxpart = h->pxpart.p; ta.l1part = h->l1part.p; ta.l2part = h->l2part.p;
-    } else {
-      ta.stats = h->stats.p; ta.rdot = h->rdot.p;
-    }
-    if (!h->plan_bwd.ready)
-      CKS(tc_backward_plan(h->tc, h->plan_bwd, h->Sxb.p, nkp, h->dYb.p, vkp, h->x3 ? 3 : 1, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
-    CKS(tc_backward_launch(h->tc, h->plan_bwd, h->n_pairs, ta, h->N, h->V, h->Ke, s, g_err, sizeof(g_err)));
-    mark(h, s, "tc_gemm_bwd_adam");
-    if (h->bf16) {
-      // Pb now holds exp(Mnew - lseT): lseT becomes the offset of the resident P
-      float* t = h->lseA; h->lseA = h->lseT; h->lseT = t;
-      h->p_state = 2;
-    }
-  } else {
-    GemmArgs g;
+    LAUNCH_CHECK("rowdot_finalize");
+    if (h->constrained) CKS(filter_update(h, s, a));
     g.A = s_act(h); g.lda = h->Ke; g.B = h->dY.p; g.ldb = h->Ke;
     g.M = h->N; g.N = h->V; g.K = h->Ke; g.k_per_split = h->Ke;
     EpiAdam epi{h->M.p, h->m.p, h->v.p, h->ld, h->V, h->stats.p, h->rdot.p, h->cfg.lambda_r, h->cfg.lambda_l1, h->cfg.lambda_l2, a};
     dim3 grid((unsigned)ceil_div(h->V, SG_BN), (unsigned)ceil_div(h->N, SG_BM), 1);
     k_gemm_simt<true, true, EpiAdam><<<grid, SG_THREADS, 0, s>>>(g, epi);
     LAUNCH_CHECK("simt_gemm_bwd_adam");
-  }
   }
   CKS(join_streams(h, caller));
   h->step++;
@@ -1142,7 +1131,6 @@ extern "C" int tgb200_get_mapping(tgb200_mapper* h, float* out, void* stream) {
   size_t cap_elems = nv;
   if (h->x3) { scratch = reinterpret_cast<float*>(h->Pb.p); cap_elems = 3 * nv / 2; }
   else if (h->staged) { scratch = reinterpret_cast<float*>(h->dq.p); cap_elems = nv / 2; }
-  else if (h->tcm) { CKS(tmp.alloc(nv, false)); scratch = tmp.p; }
   int blk = (int)(cap_elems / (size_t)h->ld);
   if (blk > h->N) blk = h->N;
   if (blk < 1) { CKS(tmp.alloc((size_t)h->ld, false)); scratch = tmp.p; blk = 1; }     // one-row mapping in staged mode
@@ -1436,47 +1424,6 @@ extern "C" int tgb200_debug_buffer(tgb200_mapper* h, const char* name, float* ou
   return TGB200_OK;
 }
 
-#ifdef TGB_EPI_TIMING
-// Dev microbenchmark: the state traffic of the backward epilogue as a pure streaming kernel
-// (read M, m, v; write M, m, v and bf16 P) -- the practical HBM ceiling for that access mix.
-__global__ void __launch_bounds__(256) k_stream_adam(float4* __restrict__ M, float4* __restrict__ m, float4* __restrict__ v,
-                                                      uint2* __restrict__ P, size_t n4) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 x = ld_stream(M + i), a = ld_stream(m + i), b = ld_stream(v + i);
-    float* xs = reinterpret_cast<float*>(&x); float* as = reinterpret_cast<float*>(&a); float* bs = reinterpret_cast<float*>(&b);
-    float pr[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float g = xs[e] * 1e-3f;
-      as[e] = fmaf(g - as[e], 0.1f, as[e]);
-      bs[e] = fmaf(0.001f * g, g, bs[e] * 0.999f);
-      xs[e] = fmaf(-0.1f * as[e], fast_rcp(fmaf(fast_sqrt(bs[e]), 1.f, 1e-8f)), xs[e]);
-      pr[e] = fast_ex2(xs[e] - 20.f);
-    }
-    st_stream(M + i, x); st_stream(m + i, a); st_stream(v + i, b);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(pr[0], pr[1]), hi = __floats2bfloat162_rn(pr[2], pr[3]);
-    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
-    P[i] = u;
-  }
-}
-extern "C" __attribute__((visibility("default"))) int tgb200_debug_stream_bench(tgb200_mapper* h, int blocks_per_sm, float* ms_out) {
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const size_t n4 = (size_t)h->N * h->ld / 4;
-  for (int rep = 0; rep < 3; ++rep) {
-    cudaEventRecord(e0);
-    k_stream_adam<<<148 * blocks_per_sm, 256>>>((float4*)h->M.p, (float4*)h->m.p, (float4*)h->v.p, (uint2*)h->Pb.p, n4);
-    cudaEventRecord(e1); cudaEventSynchronize(e1);
-    cudaEventElapsedTime(ms_out, e0, e1);
-  }
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-extern "C" __attribute__((visibility("default"))) int tgb200_debug_epi_timing(unsigned long long* out8, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, g_epi_timing, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_epi_timing, z, sizeof(z)); }
-  return 0;
-}
-#endif
 
 extern "C" int tgb200_algorithmic_cost(tgb200_mapper* h, double* hbm_bytes, double* flops) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
