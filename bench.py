@@ -33,6 +33,7 @@ WORKLOADS = {
     "c4": (256, 50_000, 5_000, 0, True, "synthetic 256 clusters x 50k voxels x 5k genes, mode=clusters"),
     "c5": (50_000, 5_000, 2_000, 32, False,
            "synthetic 50k cells x 5k voxels x 2k genes, neighbourhood + ct-islands + Getis-Ord on"),
+    "tiny": (300, 80, 50, 0, False, "synthetic 300 cells x 80 voxels x 50 genes (smoke test of the bench arms themselves)"),
 }
 C5_LAMBDAS = dict(lambda_neighborhood_g1=0.96, lambda_ct_islands=0.17, lambda_getis_ord=0.71,
                   lambda_r=2.95e-9, lambda_l2=1e-18)

@@ -64,8 +64,9 @@ class _ResultBuffer:
     """Where softmax(M) lands (mapping_optimizer.py:406-408).  A fresh 4 GB numpy array is a million page faults and a
     staged pageable copy (~0.7 s at 100k x 10k); so for large results a host thread faults the pages in and page-locks
     them WHILE the iterations run (tgb200_host_pin), and the final device->host copy is one DMA at link speed.  Results
-    under 256 MB, or a failed registration (locked-memory limit), simply use the pageable path."""
-    MIN_BYTES = 256 << 20
+    under 1 GB (where faulting + registering costs more than the staged copy it saves, and where many ranks of one node would
+    all be registering at once), or a failed registration (locked-memory limit), simply use the pageable path."""
+    MIN_BYTES = 1 << 30
 
     def __init__(self, lib, shape, device):
         self.arr = np.empty(shape, dtype=np.float32)

@@ -187,3 +187,26 @@ def test_process_group_needs_cells_mode():
     tg.pp_adatas(ad_sc, ad_sp)
     with pytest.raises(ValueError, match="only mode='cells' can be sharded"):
         tg.map_cells_to_space(ad_sc, ad_sp, mode="clusters", cluster_label="lab", process_group=object())
+
+
+def test_bench_reference_arm_runs_the_unmodified_reference_on_the_host():
+    """`bench.py --impl reference`: the unmodified reference Mapper (oracle/_ref or the reference tree) on the host cores, full
+    workload, bounded epochs; the JSON line carries what was actually run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from tests.helpers import REFERENCE_FILE
+    if not os.path.exists(REFERENCE_FILE):
+        pytest.skip("reference file not available (oracle/build_ref.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "5",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "map_cells_to_space iterations/sec" and line["unit"] == "iterations/s"
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert 2 <= line["steps"] <= 5 and line["steps_requested"] == 5 and line["value"] > 0
+    assert abs(line["value"] - 1e3 / line["ms_per_step"]) < 1e-6 * line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["cells"] == 300 and "unmodified reference" in line["cpu_baseline"]["sample"]
