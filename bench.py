@@ -40,6 +40,11 @@ C5_LAMBDAS = dict(lambda_neighborhood_g1=0.96, lambda_ct_islands=0.17, lambda_ge
 L2_BYTES = 126e6
 
 
+def shard_rows_for(n_cells, rank, world):
+    from tangram_b200.sharded import shard_rows
+    return shard_rows(n_cells, rank, world)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -416,13 +421,12 @@ def main():
     eng.init_mapping_normal(SEED, first_row=r0)      # device Philox keyed by the global cell index: same M0 at every N
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
-        # the handle's own NCCL communicator (tgb200_comm_init_rank): the per-iteration exchange runs inside tgb200_run;
-        # torch.distributed only carries the 128-byte id
-        def bcast(uid):
-            t = torch.from_numpy(uid).cuda()
-            dist.broadcast(t, src=0)
-            return t.cpu().numpy()
-        eng.comm_init(rank, world, bcast)
+        # the library's own NCCL communicator (one per process and group, tgb200_comm_create; torch.distributed only carries
+        # the 128-byte id): the per-iteration exchange runs inside tgb200_run.  Created here, before any timed region, like
+        # dist.init_process_group -- Mapper(process_group=) in the e2e leg reuses it.
+        from tangram_b200.sharded import nccl_comm_for_group
+        comm, _, _ = nccl_comm_for_group(dist.group.WORLD, local)
+        eng.set_comm(comm, rank, world)
 
     def one_step(n=1):
         eng.run(n, 0.1, stream)
@@ -593,7 +597,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "collective": ({"name": "ncclAllReduce(sum, f32) of the exchange buffer [Y_ext (voxels x Ke) | 8 row-scalar partials], in place",
                                 "bytes_per_step_per_rank": (V * (-(-(K + 2 + T) // 64) * 64) + 8) * 4, "per_step": 1,
-                                "issued_by": "tgb200_run on the handle's own stream (communicator from tgb200_comm_init_rank)"}
+                                "issued_by": "tgb200_run on the handle's own stream (communicator from tgb200_comm_create, lent with tgb200_set_comm)"}
                                if world > 1 else None),
                 "parity": parity, "reference_gpu": refgpu,
                 "vs_reference_gpu": (value / refgpu["value"]) if refgpu else None, "bf16x3": x3}

@@ -176,6 +176,10 @@ TGB200_API int tgb200_step_end(tgb200_mapper* h, float learning_rate, void* stre
 TGB200_API int tgb200_comm_unique_id(void* id_out_128_bytes, int64_t capacity);
 TGB200_API int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id_128_bytes, int32_t rank, int32_t world);
 TGB200_API int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, int32_t world);
+/* A communicator that outlives handles (ncclCommInitRank on `device`; costs a second or more at 8 ranks): create it once per
+ * process and group of ranks, lend it to every handle with tgb200_set_comm, destroy it when no handle uses it any more. */
+TGB200_API int tgb200_comm_create(const void* unique_id_128_bytes, int32_t rank, int32_t world, int32_t device, void** comm_out);
+TGB200_API int tgb200_comm_destroy(void* nccl_comm);
 
 /* ---- outputs ----------------------------------------------------------------------- */
 

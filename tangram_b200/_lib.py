@@ -60,6 +60,8 @@ SIGNATURES = {
     "tgb200_comm_unique_id": (ctypes.c_int, [_P, ctypes.c_int64]),
     "tgb200_comm_init_rank": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "tgb200_set_comm": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
+    "tgb200_comm_create": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P)]),
+    "tgb200_comm_destroy": (ctypes.c_int, [_P]),
     "tgb200_history_len": (ctypes.c_int, [_P, _I64]),
     "tgb200_get_history": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64, _P, _P]),
     "tgb200_get_mapping": (ctypes.c_int, [_P, _P, _P]),

@@ -175,6 +175,7 @@ struct TileCoord {
 
 struct TcEpiStore {
   float* C; int ldc; size_t split_stride; int M;
+  int accumulate;        // 1: C += tile (cell chunks of the pipelined forward run one after the other: fixed summation order)
   template <int BN, int NW>
   __device__ __forceinline__ void prologue(const TileCoord&, int, int, int) const {}
   __device__ __forceinline__ void finish(int, int, int) const {}
@@ -189,6 +190,13 @@ struct TcEpiStore {
       const int col = t.n0 + c;
       if (row < M && col < ldc) {
         float4* dst = reinterpret_cast<float4*>(C + (size_t)t.split * split_stride + (size_t)row * ldc + col);
+        if (accumulate) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 o = dst[e];
+            v[4 * e] += o.x; v[4 * e + 1] += o.y; v[4 * e + 2] += o.z; v[4 * e + 3] += o.w;
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
       }
@@ -813,20 +821,20 @@ static inline int tc_forward_launch(TcContext& tc, const TcPlan& pl, int n_pairs
   auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
   const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
-  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
+  TcEpiStore epi{out, Ke, (size_t)V * Ke, V, 0};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
   kern<<<tc_grid(tc, (long long)tm * tn * splits), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, n_pairs, N, tc_kps(N, splits), tm, tn,
                                                                          splits, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, 0, epi);
   return tc_check_launch("tc_gemm_fwd", err, n);
 }
-// cells [row0, row1) only (row0 a multiple of 64): partial sum into `out` -- the host pipelines cell chunks behind the
-// streaming Adam kernel and k_loss_reduce adds the planes
-static inline int tc_forward_launch_rows(TcContext& tc, const TcPlan& pl, float* out, int row0, int row1, int V, int Ke, cudaStream_t s,
-                                         char* err, size_t n) {
+// cells [row0, row1) only (row0 a multiple of 64): `out` = or += this chunk's partial sum -- the host pipelines cell chunks
+// behind the streaming Adam kernel; the chunks run one after the other on one stream, so the summation order is fixed
+static inline int tc_forward_launch_rows(TcContext& tc, const TcPlan& pl, float* out, int accumulate, int row0, int row1, int V, int Ke,
+                                         cudaStream_t s, char* err, size_t n) {
   auto kern = k_gemm_tc<false, false, TC_FWD_BN, TC_FWD_STAGES, 4, TcEpiStore>;
   const int smem = TC_FWD_STAGES * (TC_BM + TC_FWD_BN) * TC_BK * 2 + 1024;
   if (tc_set_smem(tc, kern, smem, err, n)) return -2;
-  TcEpiStore epi{out, Ke, (size_t)V * Ke, V};
+  TcEpiStore epi{out, Ke, (size_t)V * Ke, V, accumulate};
   const int tm = (int)ceil_div(V, TC_BM), tn = (int)ceil_div(Ke, TC_FWD_BN);
   kern<<<tc_grid(tc, (long long)tm * tn), 64 + 32 * 4, smem, s>>>(pl.a, pl.b, 1, row1, (int)round_up(row1 - row0, TC_BK), tm, tn,
                                                                 1, 1, kPolicyEvictNormal, kPolicyEvictNormal, 0, row0, epi);

@@ -345,7 +345,7 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     if (s < 1) s = 1;
     if (h->tcm) s = tc_forward_splits(h->N, h->V, h->Ke);
     if (h->x3) { const int c = tc_splits_for_chain(h->N, 2048); if (c > s) s = c; }
-    if (h->nchunks > 1) s = h->nchunks;      // one partial plane per cell chunk (k_loss_reduce adds them)
+    if (h->nchunks > 1) s = 1;               // the cell chunks of the pipelined forward accumulate straight into Y_ext
     h->fwd_splits = s;
     if (s > 1) A(h->Ypart.alloc((size_t)s * vk));
   }
@@ -741,7 +741,8 @@ static int forward_chunk(tgb200_mapper* h, cudaStream_t s, int c, int fresh, con
   k_scale_rows_bf16<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(s_act(h), h->inv_zt.p, r0, r1, h->Ke, h->Sxs.p);
   LAUNCH_CHECK("scale_rows");
   if (h->nchunks > 1) {
-    CKS(tc_forward_launch_rows(h->tc, h->plan_fwd, h->Ypart.p + (size_t)c * h->V * h->Ke, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
+    // chunk 0 overwrites the exchange buffer, the others add to it (same stream, fixed order): no partial planes to sum
+    CKS(tc_forward_launch_rows(h->tc, h->plan_fwd, h->Y.p, c > 0 ? 1 : 0, r0, r1, h->V, h->Ke, s, g_err, sizeof(g_err)));
     mark(h, s, "tc_gemm_fwd");
   }
   return TGB200_OK;
@@ -1063,6 +1064,31 @@ extern "C" int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id, in
   return TGB200_OK;
 }
 
+// A communicator that outlives handles: created once per process and group of ranks, lent to handles with tgb200_set_comm
+// (ncclCommInitRank costs a second or more at 8 ranks -- too much to pay in every Mapper constructor).
+extern "C" int tgb200_comm_create(const void* unique_id, int32_t rank, int32_t world, int32_t device, void** comm_out) {
+  if (!unique_id || !comm_out) return fail(TGB200_ERR_INVALID, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(TGB200_ERR_INVALID, "bad rank %d of %d", rank, world);
+  NcclApi* api = nccl_api(g_err, sizeof(g_err));
+  if (!api) return TGB200_ERR_STATE;
+  CK(cudaSetDevice(device));
+  NcclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) return fail(TGB200_ERR_CUDA, "ncclCommInitRank: %s", api->GetErrorString(r));
+  *comm_out = comm;
+  return TGB200_OK;
+}
+extern "C" int tgb200_comm_destroy(void* comm) {
+  if (!comm) return TGB200_OK;
+  NcclApi* api = nccl_api(g_err, sizeof(g_err));
+  if (!api) return TGB200_ERR_STATE;
+  const int r = api->CommDestroy(comm);
+  if (r != 0) return fail(TGB200_ERR_CUDA, "ncclCommDestroy: %s", api->GetErrorString(r));
+  return TGB200_OK;
+}
+
 extern "C" int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, int32_t world) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   if (nccl_comm && (world < 1 || rank < 0 || rank >= world)) return fail(TGB200_ERR_INVALID, "bad rank %d of %d", rank, world);
@@ -1075,7 +1101,9 @@ extern "C" int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, 
 extern "C" int tgb200_run(tgb200_mapper* h, int32_t n_steps, float lr, void* stream) {
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   if (n_steps < 0) return fail(TGB200_ERR_INVALID, "n_steps < 0");
-  const bool sharded = h->cfg.n_cells_global != h->N;
+  // TGB200_SKIP_EXCHANGE=1 (dev only): run one rank's share of a sharded iteration on a single GPU without its collective
+  static const bool kSkipExchange = getenv("TGB200_SKIP_EXCHANGE") && atoi(getenv("TGB200_SKIP_EXCHANGE")) != 0;
+  const bool sharded = h->cfg.n_cells_global != h->N && !kSkipExchange;
   if (sharded && !h->comm)
     return fail(TGB200_ERR_STATE, "cell-sharded handle without a communicator: call tgb200_comm_init_rank / tgb200_set_comm, or drive "
                                   "step_begin / all-reduce / step_end yourself");

@@ -88,6 +88,10 @@ class Engine:
         uid = np.ascontiguousarray(broadcast(uid), dtype=np.uint8)
         _lib.check(self._lib.tgb200_comm_init_rank(self._h, _lib.ptr(uid), rank, world))
 
+    def set_comm(self, comm, rank, world):
+        """Lend the handle an existing ncclComm_t (tangram_b200.sharded.nccl_comm_for_group); the caller keeps ownership."""
+        _lib.check(self._lib.tgb200_set_comm(self._h, comm, rank, world))
+
     def exchange_tensor(self):
         import torch
         p, n = ctypes.c_void_p(), ctypes.c_int64()

@@ -264,21 +264,15 @@ class Mapper:
             self._init_comm(process_group)
 
     def _init_comm(self, pg):
-        """One NCCL communicator per handle (tgb200_comm_init_rank): rank 0 of the group makes the 128-byte unique id,
-        torch.distributed only carries it to the other ranks.  Non-NCCL groups (gloo in the CPU tests) keep the
-        host-driven exchange of tangram_b200.sharded."""
-        import torch
-        import torch.distributed as dist
-        if dist.get_backend(pg) != "nccl":
+        """NCCL group: lend the handle the process-level communicator of this group (tangram_b200.sharded.nccl_comm_for_group,
+        created once) so that tgb200_run issues the per-iteration exchange itself.  Non-NCCL groups (gloo in the CPU tests)
+        keep the host-driven exchange of tangram_b200.sharded."""
+        from .sharded import nccl_comm_for_group
+        got = nccl_comm_for_group(pg, self._cfg.device)
+        if got is None:
             return
-        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
-        uid = np.zeros(128, dtype=np.uint8)
-        if rank == 0:
-            _lib.check(self._lib.tgb200_comm_unique_id(_lib.ptr(uid), uid.nbytes))
-        t = torch.from_numpy(uid).to(f"cuda:{self._cfg.device}")
-        dist.broadcast(t, src=dist.get_global_rank(pg, 0), group=pg)
-        uid = t.cpu().numpy()
-        _lib.check(self._lib.tgb200_comm_init_rank(self._h, _lib.ptr(uid), rank, world))
+        comm, rank, world = got
+        _lib.check(self._lib.tgb200_set_comm(self._h, comm, rank, world))
         self._own_comm = True
 
     # ------------------------------------------------------------------------------

@@ -25,3 +25,52 @@ def sharded_steps(engine, n_steps, lr, all_reduce):
         engine.step_begin()
         all_reduce(buf)
         engine.step_end(lr)
+
+
+# ---- NCCL communicators for the in-library exchange, one per (process group, device), kept for the life of the process ----
+_COMMS = {}
+
+
+def nccl_comm_for_group(pg, device):
+    """(ncclComm_t as int, rank, world) for a torch.distributed NCCL group: created on first use (rank 0 makes the 128-byte
+    unique id with tgb200_comm_unique_id, one dist.broadcast carries it), then reused by every Mapper / Engine of this
+    process -- ncclCommInitRank takes a second or more at 8 ranks.  Returns None for non-NCCL groups (gloo in the CPU tests),
+    which keep the host-driven exchange of `sharded_steps`."""
+    import atexit
+    import ctypes
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    if dist.get_backend(pg) != "nccl":
+        return None
+    key = (id(pg), int(device))
+    if key not in _COMMS:
+        lib = _lib.load()
+        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(lib.tgb200_comm_unique_id(_lib.ptr(uid), uid.nbytes))
+        t = torch.from_numpy(uid).to(f"cuda:{int(device)}")
+        dist.broadcast(t, src=dist.get_global_rank(pg, 0), group=pg)
+        uid = np.ascontiguousarray(t.cpu().numpy())
+        comm = ctypes.c_void_p()
+        _lib.check(lib.tgb200_comm_create(_lib.ptr(uid), rank, world, int(device), ctypes.byref(comm)))
+        if not _COMMS:
+            atexit.register(_destroy_comms)
+        _COMMS[key] = (comm, rank, world, pg)          # pg kept alive: id(pg) stays unique
+    comm, rank, world, _ = _COMMS[key]
+    return comm, rank, world
+
+
+def _destroy_comms():
+    from . import _lib
+    try:
+        lib = _lib.load()
+        for comm, _, _, _ in _COMMS.values():
+            lib.tgb200_comm_destroy(comm)
+    except Exception:  # noqa: BLE001  (interpreter shutdown)
+        pass
+    _COMMS.clear()
