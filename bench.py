@@ -597,7 +597,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "collective": ({"name": "ncclAllReduce(sum, f32) of the exchange buffer [Y_ext (voxels x Ke) | 8 row-scalar partials], in place",
                                 "bytes_per_step_per_rank": (V * (-(-(K + 2 + T) // 64) * 64) + 8) * 4, "per_step": 1,
-                                "issued_by": "tgb200_run on the handle's own stream (communicator from tgb200_comm_create, lent with tgb200_set_comm)"}
+                                "issued_by": "tgb200_run on the handle's own stream (communicator from tgb200_comm_create, lent with tgb200_set_comm); the buffer "
+                                             "lives in ncclMemAlloc memory registered with the communicator (NVLS in-switch reduction on user buffers)"}
                                if world > 1 else None),
                 "parity": parity, "reference_gpu": refgpu,
                 "vs_reference_gpu": (value / refgpu["value"]) if refgpu else None, "bf16x3": x3}

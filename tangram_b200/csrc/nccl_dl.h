@@ -23,6 +23,12 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  // optional (NCCL >= 2.19): memory NCCL can map into the NVSwitch multicast space + user-buffer registration, so that an
+  // in-place all-reduce of that buffer runs in the switch (NVLS) without staging copies
+  int (*MemAlloc)(void**, size_t) = nullptr;
+  int (*MemFree)(void*) = nullptr;
+  int (*CommRegister)(void*, void*, size_t, void**) = nullptr;
+  int (*CommDeregister)(void*, void*) = nullptr;
   bool ok() const { return lib != nullptr; }
 };
 
@@ -50,6 +56,10 @@ static inline NcclApi* nccl_api(char* err, size_t n) {
   a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
   if (!good) { snprintf(err, n, "libnccl.so.2 lacks an expected entry point"); return nullptr; }
+  a.MemAlloc = reinterpret_cast<decltype(a.MemAlloc)>(dlsym(lib, "ncclMemAlloc"));
+  a.MemFree = reinterpret_cast<decltype(a.MemFree)>(dlsym(lib, "ncclMemFree"));
+  a.CommRegister = reinterpret_cast<decltype(a.CommRegister)>(dlsym(lib, "ncclCommRegister"));
+  a.CommDeregister = reinterpret_cast<decltype(a.CommDeregister)>(dlsym(lib, "ncclCommDeregister"));
   api = a;
   return &api;
 }

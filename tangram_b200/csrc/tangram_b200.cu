@@ -162,7 +162,19 @@ struct tgb200_mapper {
   void* comm = nullptr;
   bool comm_owned = false;
   int comm_rank = 0, comm_world = 1;
+  bool y_nccl = false;          // the exchange buffer lives in ncclMemAlloc memory registered with `comm`
+  void* y_reg = nullptr;
+  void release_exchange_registration() {
+    if (!y_nccl) return;
+    char e[64];
+    if (NcclApi* a = nccl_api(e, sizeof(e))) {
+      if (y_reg && comm) a->CommDeregister(comm, y_reg);
+      a->MemFree(Y.p);
+    }
+    Y.p = nullptr; Y.n = 0; y_nccl = false; y_reg = nullptr;
+  }
   ~tgb200_mapper() {
+    release_exchange_registration();
     if (comm && comm_owned) { char e[64]; if (NcclApi* a = nccl_api(e, sizeof(e))) a->CommDestroy(comm); }
     if (hi) cudaStreamDestroy(hi);
     if (lo) cudaStreamDestroy(lo);
@@ -1037,6 +1049,27 @@ static int exchange_partials(tgb200_mapper* h, cudaStream_t s) {
   return TGB200_OK;
 }
 
+// With a communicator in hand, move the exchange buffer into memory NCCL allocated itself and register it: the in-place
+// all-reduce then runs as an in-switch (NVLS) reduction on user buffers.  Best effort: any failure keeps the plain buffer.
+static void register_exchange_buffer(tgb200_mapper* h) {
+  static const bool kOn = !(getenv("TGB200_NCCL_REGISTER") && atoi(getenv("TGB200_NCCL_REGISTER")) == 0);
+  char e[128];
+  NcclApi* a = nccl_api(e, sizeof(e));
+  if (!kOn || !a || !a->MemAlloc || !a->MemFree || !a->CommRegister || !a->CommDeregister || h->y_nccl || !h->comm) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  void* buf = nullptr;
+  const size_t bytes = h->Y.n * sizeof(float);
+  if (a->MemAlloc(&buf, bytes) != 0 || !buf) { (void)cudaGetLastError(); return; }
+  if (cudaMemcpy(buf, h->Y.p, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) { a->MemFree(buf); (void)cudaGetLastError(); return; }
+  void* reg = nullptr;
+  if (a->CommRegister(h->comm, buf, bytes, &reg) != 0) { a->MemFree(buf); (void)cudaGetLastError(); return; }
+  const size_t n = h->Y.n;
+  h->Y.release();
+  h->Y.p = static_cast<float*>(buf); h->Y.n = n;
+  h->y_nccl = true; h->y_reg = reg;
+}
+
 extern "C" int tgb200_comm_unique_id(void* id_out, int64_t cap) {
   if (!id_out || cap < (int64_t)sizeof(NcclUniqueId)) return fail(TGB200_ERR_INVALID, "id buffer must hold %zu bytes", sizeof(NcclUniqueId));
   NcclApi* api = nccl_api(g_err, sizeof(g_err));
@@ -1061,6 +1094,7 @@ extern "C" int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id, in
   const int r = api->CommInitRank(&comm, world, id, rank);
   if (r != 0) return fail(TGB200_ERR_CUDA, "ncclCommInitRank: %s", api->GetErrorString(r));
   h->comm = comm; h->comm_owned = true; h->comm_rank = rank; h->comm_world = world;
+  register_exchange_buffer(h);
   return TGB200_OK;
 }
 
@@ -1093,8 +1127,17 @@ extern "C" int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, 
   if (!h) return fail(TGB200_ERR_INVALID, "null handle");
   if (nccl_comm && (world < 1 || rank < 0 || rank >= world)) return fail(TGB200_ERR_INVALID, "bad rank %d of %d", rank, world);
   if (nccl_comm && !nccl_api(g_err, sizeof(g_err))) return TGB200_ERR_STATE;
+  if (h->y_nccl) {              // back to a plain buffer before the communicator it is registered with goes away
+    DevBuf<float> plain;
+    CKS(plain.alloc(h->Y.n, false));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(plain.p, h->Y.p, h->Y.n * sizeof(float), cudaMemcpyDeviceToDevice));
+    h->release_exchange_registration();
+    h->Y.p = plain.p; h->Y.n = plain.n; plain.p = nullptr; plain.n = 0;
+  }
   if (h->comm && h->comm_owned) { if (NcclApi* a = nccl_api(g_err, sizeof(g_err))) a->CommDestroy(h->comm); }
   h->comm = nccl_comm; h->comm_owned = false; h->comm_rank = rank; h->comm_world = nccl_comm ? world : 1;
+  register_exchange_buffer(h);
   return TGB200_OK;
 }
 

@@ -32,11 +32,11 @@ _COMMS = {}
 
 
 def nccl_comm_for_group(pg, device):
-    """(ncclComm_t as int, rank, world) for a torch.distributed NCCL group: created on first use (rank 0 makes the 128-byte
+    """(ncclComm_t, rank, world) for a torch.distributed NCCL group: created on first use (rank 0 makes the 128-byte
     unique id with tgb200_comm_unique_id, one dist.broadcast carries it), then reused by every Mapper / Engine of this
     process -- ncclCommInitRank takes a second or more at 8 ranks.  Returns None for non-NCCL groups (gloo in the CPU tests),
-    which keep the host-driven exchange of `sharded_steps`."""
-    import atexit
+    which keep the host-driven exchange of `sharded_steps`.  The communicators are deliberately not destroyed at interpreter
+    exit (handles that borrowed one may be finalised later; the process is going away anyway)."""
     import ctypes
 
     import numpy as np
@@ -58,19 +58,6 @@ def nccl_comm_for_group(pg, device):
         uid = np.ascontiguousarray(t.cpu().numpy())
         comm = ctypes.c_void_p()
         _lib.check(lib.tgb200_comm_create(_lib.ptr(uid), rank, world, int(device), ctypes.byref(comm)))
-        if not _COMMS:
-            atexit.register(_destroy_comms)
         _COMMS[key] = (comm, rank, world, pg)          # pg kept alive: id(pg) stays unique
     comm, rank, world, _ = _COMMS[key]
     return comm, rank, world
-
-
-def _destroy_comms():
-    from . import _lib
-    try:
-        lib = _lib.load()
-        for comm, _, _, _ in _COMMS.values():
-            lib.tgb200_comm_destroy(comm)
-    except Exception:  # noqa: BLE001  (interpreter shutdown)
-        pass
-    _COMMS.clear()

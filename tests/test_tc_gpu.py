@@ -202,3 +202,47 @@ def test_more_than_65535_voxels(precision):
     assert out.shape == (N, V) and np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
     assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < (2e-3 if precision == "bf16" else 2e-5)
     assert rel_fro(out, oo) < (5e-2 if precision == "bf16" else 1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_manual_exchange_protocol_two_shards_on_one_gpu(precision):
+    """The C-ABI's caller-driven sharded loop (tgb200_step_begin -> all-reduce of the exchange buffer -> tgb200_step_end):
+    two handles hold the two halves of the cells on ONE GPU, the test plays the all-reduce by summing their exchange buffers.
+    Must reproduce the unsharded handle (same arithmetic up to the order of the cell sum)."""
+    import torch
+    from tangram_b200.engine import Engine
+    from tangram_b200.sharded import shard_rows
+    N, V, K, steps = 2304, 300, 120, 5
+    inp = synthetic_inputs(N, V, K, seed=23)
+    M0 = np.random.default_rng(3).standard_normal((N, V)).astype(np.float32)
+    kw = dict(precision=precision, lambda_r=1e-3)
+
+    def make(r0, r1):
+        e = Engine(r1 - r0, V, K, n_cells_global=N, **kw)
+        e.set_expression(np.ascontiguousarray(inp["S"][r0:r1]), inp["G"])
+        e.set_density(inp["d"])
+        e.set_mapping(np.ascontiguousarray(M0[r0:r1]))
+        return e
+
+    whole = make(0, N)
+    whole.run(steps)
+    ref = np.empty((N, V), dtype=np.float32)
+    whole.get_mapping(ref)
+    parts = [make(*shard_rows(N, r, 2)) for r in range(2)]
+    bufs = [p.exchange_tensor() for p in parts]
+    for _ in range(steps):
+        for p in parts:
+            p.step_begin()
+        torch.cuda.synchronize()
+        total = bufs[0] + bufs[1]
+        for b in bufs:
+            b.copy_(total)
+        torch.cuda.synchronize()
+        for p in parts:
+            p.step_end(0.1)
+    got = np.concatenate([p.get_mapping(np.empty((p.cfg.n_cells, V), dtype=np.float32)) for p in parts])
+    tol = 2e-2 if precision == "bf16" else 2e-5
+    assert rel_fro(got, ref) < tol
+    hw, hp = whole.history()[:, 0], parts[0].history()[:, 0]
+    assert np.max(np.abs(hw - hp)) < (1e-3 if precision == "bf16" else 1e-5)
+    assert np.array_equal(parts[0].history()[:, :5], parts[1].history()[:, :5], equal_nan=True)     # every rank logs the global loss
