@@ -172,7 +172,11 @@ TGB200_API int tgb200_step_end(tgb200_mapper* h, float learning_rate, void* stre
  * process, e.g. PyTorch's, else the system one).
  *   tgb200_comm_unique_id   rank 0: 128 opaque bytes (ncclGetUniqueId) to hand to every rank by any means
  *   tgb200_comm_init_rank   every rank: ncclCommInitRank on the handle's device; the handle owns the communicator
- *   tgb200_set_comm         alternatively borrow an existing ncclComm_t (NULL detaches); the caller keeps ownership */
+ *   tgb200_set_comm         alternatively borrow an existing ncclComm_t (NULL detaches); the caller keeps ownership and must
+ *                           detach or destroy the handle before destroying that communicator
+ * When a communicator arrives the exchange buffer is moved into ncclMemAlloc memory and registered with it (ncclCommRegister,
+ * NCCL >= 2.19; silently skipped otherwise), so that the in-place all-reduce runs as an in-switch NVLS reduction on user
+ * buffers; pointers obtained earlier from tgb200_exchange_buffer are invalid afterwards. */
 TGB200_API int tgb200_comm_unique_id(void* id_out_128_bytes, int64_t capacity);
 TGB200_API int tgb200_comm_init_rank(tgb200_mapper* h, const void* unique_id_128_bytes, int32_t rank, int32_t world);
 TGB200_API int tgb200_set_comm(tgb200_mapper* h, void* nccl_comm, int32_t rank, int32_t world);

@@ -331,6 +331,8 @@ extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
     while (nc > 1 && h->N / nc < 1024) --nc;
     h->nchunks = nc;
     for (int c = 0; c <= nc; ++c) h->chunk_row[c] = c == nc ? h->N : (int)round_up((int64_t)c * h->N / nc, 256);
+  }
+  if (h->staged && h->nchunks > 1) {          // one chunk: nothing to overlap, everything stays on the caller's stream
     int lo_p = 0, hi_p = 0;
     cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
     // priorities: backward contractions (they feed the streaming update) > next forward's chunks > the update itself
