@@ -11,4 +11,4 @@ from .mapping_utils import (  # noqa: F401
 from .utils import project_genes  # noqa: F401
 from .adata import MiniAnnData  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -250,7 +250,7 @@ extern "C" int tgb200_host_unpin(void* buf) {
   return TGB200_OK;
 }
 extern "C" const char* tgb200_last_error(void) { return g_err; }
-extern "C" const char* tgb200_version(void) { return "tangram_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* tgb200_version(void) { return "tangram_b200 0.2.0 (sm_100a)"; }
 
 extern "C" int tgb200_create(const tgb200_config* cfg, tgb200_mapper** out) {
   if (!cfg || !out) return fail(TGB200_ERR_INVALID, "null argument");
@@ -739,7 +739,7 @@ static int join_streams(tgb200_mapper* h, cudaStream_t s) {
 }
 
 // bf16 mode, cells of chunk c: exact row statistics from the sums the update left (k_row_norm), the scaled forward operand,
-// and -- when the forward is chunked -- this chunk's partial plane of Y_ext.  `lseA` / `lseT` as they are for THAT forward.
+// and -- when the forward is chunked -- this chunk's contribution to Y_ext.  `lseA` / `lseT` as they are for THAT forward.
 static int forward_chunk(tgb200_mapper* h, cudaStream_t s, int c, int fresh, const float* lseA, float* lseT) {
   float* rowaux = needs_rowaux(h->cfg) ? h->rowaux.p : nullptr;
   if (!h->plan_fwd.ready)

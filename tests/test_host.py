@@ -210,3 +210,55 @@ def test_bench_reference_arm_runs_the_unmodified_reference_on_the_host():
     assert abs(line["value"] - 1e3 / line["ms_per_step"]) < 1e-6 * line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["cells"] == 300 and "unmodified reference" in line["cpu_baseline"]["sample"]
+
+
+def test_oracle_ref_recipe_is_a_verbatim_copy():
+    """oracle/build_ref.py: oracle/_ref/mapping_optimizer.py is the reference file byte for byte (sha256 in SOURCE.txt) and loads
+    as a module with the reference's two classes."""
+    import hashlib
+    import os
+    from oracle import build_ref
+    if not os.path.exists(build_ref.REF_SRC) and not os.path.exists(build_ref.REF_DST):
+        pytest.skip("neither the reference tree nor a copy is present")
+    path = build_ref.build()
+    assert path == build_ref.REF_DST and os.path.exists(path)
+    digest = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    assert digest in open(build_ref.STAMP).read()
+    if os.path.exists(build_ref.REF_SRC):
+        assert open(path, "rb").read() == open(build_ref.REF_SRC, "rb").read()
+    mod = build_ref.load()
+    assert hasattr(mod, "Mapper") and hasattr(mod, "MapperConstrained")
+
+
+def test_profiles_traffic_json_matches_the_committed_ncu_capture():
+    """bench.py's roofline.traffic comes from profiles/traffic.json, which tools/ncu_traffic.py derives from the committed raw
+    `ncu --set full` page: re-derive it and compare (DRAM bytes of the streaming update = its algorithmic 24 B/element)."""
+    import csv
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    traffic = json.load(open(os.path.join(root, "profiles", "traffic.json")))["c3/bf16"]
+    rows = list(csv.reader(open(os.path.join(root, traffic["_source"]))))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    per_launch = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]] for r in rows[2:] if "k_adam_rows" in r[ki]]
+    assert per_launch and abs(4 * np.mean(per_launch) - traffic["adam_rows"]) < 1e-6 * traffic["adam_rows"]
+    assert abs(traffic["adam_rows"] - 24.0 * 100_000 * 10_000) < 0.02 * 24e9          # nothing is re-read
+
+
+def test_nccl_comm_cache_ignores_non_nccl_groups():
+    """gloo groups (the CPU tests) keep the host-driven exchange: nccl_comm_for_group returns None without touching CUDA."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from tangram_b200.sharded import nccl_comm_for_group
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        assert nccl_comm_for_group(dist.group.WORLD, 0) is None
+    finally:
+        dist.destroy_process_group()
