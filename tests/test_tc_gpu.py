@@ -246,3 +246,24 @@ def test_manual_exchange_protocol_two_shards_on_one_gpu(precision):
     hw, hp = whole.history()[:, 0], parts[0].history()[:, 0]
     assert np.max(np.abs(hw - hp)) < (1e-3 if precision == "bf16" else 1e-5)
     assert np.array_equal(parts[0].history()[:, :5], parts[1].history()[:, :5], equal_nan=True)     # every rank logs the global loss
+
+
+def test_validation_terms_bf16_with_entropy_term_off():
+    """_val_loss_fn (mapping_optimizer.py:311-356) in the throughput mode with lambda_r == 0: the per-row entropy is not carried
+    across iterations there, so tgb200_validation_terms re-runs the exact row pass; val_entropy must be the real value (it
+    was -0.0 before), the similarity terms track the oracle at bf16 accuracy."""
+    from tangram_b200 import Mapper
+    inp = synthetic_inputs(900, 160, 80, seed=6)
+    kw = dict(S=inp["S"], G=inp["G"], d=inp["d"], lambda_d=1.0)
+    o = OracleMapper(random_state=9, **kw)
+    M0 = o.M.numpy().copy()
+    _, oh = o.train(6, print_each=None, val_each=2)
+    m = Mapper(M0=M0, device="cuda:0", precision="bf16", **kw)
+    _, hist = m.train(6, print_each=None, val_each=2)
+    for k in ("val_total_loss", "val_gene_sim", "val_sp_sparsity_weighted_sim", "val_entropy"):
+        assert len(hist[k]) == len(oh[k]) == 3
+        assert max_rel(hist[k], oh[k]) < 5e-3, (k, hist[k], oh[k])
+    assert all(v > 0.5 for v in hist["val_entropy"])                 # normalised entropy of a near-uniform mapping, not -0.0
+    # the training trajectory is not disturbed by the validation passes
+    _, h2 = Mapper(M0=M0, device="cuda:0", precision="bf16", **kw).train(6, print_each=None)
+    assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in h2["total_loss"]]) < 2e-4
