@@ -267,3 +267,53 @@ def test_validation_terms_bf16_with_entropy_term_off():
     # the training trajectory is not disturbed by the validation passes
     _, h2 = Mapper(M0=M0, device="cuda:0", precision="bf16", **kw).train(6, print_each=None)
     assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in h2["total_loss"]]) < 2e-4
+
+
+def _fuzz_cases(n=14, seed=2024):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n):
+        N = int(rng.choice([1, 7, 130, 300, 1000, 2047, 2049, 2300, 4100, 5000]))
+        V = int(rng.choice([1, 3, 63, 65, 250, 257, 640, 1000, 1500]))
+        K = int(rng.choice([1, 2, 61, 62, 63, 100, 190, 300]))
+        cases.append((N, V, K, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}-{'c' if c[3] else 'n'}{'r' if c[4] else ''}{'l' if c[5] else ''}")
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_random_shapes_against_oracle(case, precision):
+    """Seeded shape fuzz over tile / pair / chunk / padding boundaries (cells around 2048, voxels around multiples of 64 and 256,
+    genes around Ke = 64 boundaries), cells or clusters density, entropy and L1/L2 terms on or off: three epochs vs the oracle."""
+    import os
+    from tangram_b200 import Mapper
+    N, V, K, clusters, ent, l12, seed = case
+    rng = np.random.default_rng(seed)
+    S = (rng.random((N, K)) * (rng.random((N, K)) < 0.6) + 0.05).astype(np.float32)
+    G = (rng.random((V, K)) * 2 + 0.05).astype(np.float32)
+    kw = dict(S=S, G=G, lambda_d=1.0)
+    if clusters:
+        w = rng.random(N) + 0.1
+        kw.update(d=(np.ones(V) / V).astype(np.float32), d_source=(w / w.sum()).astype(np.float32))
+    else:
+        kw.update(d=(G.sum(axis=1) / G.sum()).astype(np.float32))
+    if ent:
+        kw["lambda_r"] = 1e-3
+    if l12:
+        kw.update(lambda_l1=1e-6, lambda_l2=1e-6)
+    M0 = rng.standard_normal((N, V)).astype(np.float32)
+    oo, oh = OracleMapper(M0=M0, **kw).train(3, print_each=None)
+    old = os.environ.get("TGB200_CHUNKS")
+    os.environ["TGB200_CHUNKS"] = "3"           # cells permitting, the three-stream chunk pipeline
+    try:
+        out, hist = Mapper(M0=M0, device="cuda:0", precision=precision, **kw).train(3, print_each=None)
+    finally:
+        if old is None:
+            del os.environ["TGB200_CHUNKS"]
+        else:
+            os.environ["TGB200_CHUNKS"] = old
+    assert np.all(np.isfinite(out)) and np.allclose(out.sum(axis=1), 1.0, atol=2e-5)
+    tl, ol = np.array([float(x) for x in hist["total_loss"]]), np.array([float(x) for x in oh["total_loss"]])
+    scale = max(1.0, float(np.max(np.abs(ol))))
+    assert np.max(np.abs(tl - ol)) < (5e-3 if precision == "bf16" else 2e-5) * scale, (tl, ol)
+    assert rel_fro(out, oo) < (6e-2 if precision == "bf16" else 5e-5)
