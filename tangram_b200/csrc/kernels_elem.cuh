@@ -55,8 +55,8 @@ __global__ void k_split3(const float* __restrict__ src, Split3 dst, long long n4
   store_split4(dst, (size_t)q * 4, v.x, v.y, v.z, v.w);
 }
 
-template <typename PT, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS)
+template <typename PT, int THREADS, int ITEMS, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, int ldp,
                RowStat* __restrict__ stats, float* __restrict__ rowaux /* [N][2] or null */,
                int want_entropy, Split3 split /* base == null: none */) {
@@ -69,11 +69,20 @@ k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, 
   float4 x[NI];
 
   float mx = -INFINITY, s1 = 0.f, s2 = 0.f;
+  const bool aux = rowaux != nullptr;
   auto visit_max = [&](const float4& v, int c) {
-    if (c + 0 < V) { mx = fmaxf(mx, v.x); s1 += fabsf(v.x); s2 += v.x * v.x; }
-    if (c + 1 < V) { mx = fmaxf(mx, v.y); s1 += fabsf(v.y); s2 += v.y * v.y; }
-    if (c + 2 < V) { mx = fmaxf(mx, v.z); s1 += fabsf(v.z); s2 += v.z * v.z; }
-    if (c + 3 < V) { mx = fmaxf(mx, v.w); s1 += fabsf(v.w); s2 += v.w * v.w; }
+    if (c + 3 < V) {                          // interior group: no per-element bounds checks
+      mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      if (aux) {
+        s1 += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      if (c + 0 < V) { mx = fmaxf(mx, v.x); s1 += fabsf(v.x); s2 += v.x * v.x; }
+      if (c + 1 < V) { mx = fmaxf(mx, v.y); s1 += fabsf(v.y); s2 += v.y * v.y; }
+      if (c + 2 < V) { mx = fmaxf(mx, v.z); s1 += fabsf(v.z); s2 += v.z * v.z; }
+      if (c + 3 < V) { mx = fmaxf(mx, v.w); s1 += fabsf(v.w); s2 += v.w * v.w; }
+    }
   };
   if (kCached) {
 #pragma unroll
@@ -88,22 +97,38 @@ k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, 
   }
   mx = block_reduce<true>(mx, sh);
 
+  // e_j = exp(M_ij - max): computed ONCE per element.  Without the entropy term the cached row is overwritten by e (padding
+  // = 0), so the emit pass below is a multiply; with it the pass needs M_ij - max again and recomputes (same bits either way:
+  // P_ij = expf(M_ij - max) * (1 / Z) is softmax_prob()).
   float z = 0.f;
-  auto visit_sum = [&](const float4& v, int c) {
-    if (c + 0 < V) z += expf(v.x - mx);
-    if (c + 1 < V) z += expf(v.y - mx);
-    if (c + 2 < V) z += expf(v.z - mx);
-    if (c + 3 < V) z += expf(v.w - mx);
+  auto exp4 = [&](const float4& v, int c) -> float4 {
+    float4 e;
+    if (c + 3 < V) {
+      e = make_float4(expf(v.x - mx), expf(v.y - mx), expf(v.z - mx), expf(v.w - mx));
+    } else {
+      e.x = (c + 0 < V) ? expf(v.x - mx) : 0.f;
+      e.y = (c + 1 < V) ? expf(v.y - mx) : 0.f;
+      e.z = (c + 2 < V) ? expf(v.z - mx) : 0.f;
+      e.w = (c + 3 < V) ? expf(v.w - mx) : 0.f;
+    }
+    return e;
   };
+  const bool keep_e = kCached && !want_entropy;
   if (kCached) {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int q = threadIdx.x + i * THREADS;
-      if (q < nvec) visit_sum(x[i], q * 4);
+      if (q < nvec) {
+        const float4 e = exp4(x[i], q * 4);
+        z += (e.x + e.y) + (e.z + e.w);
+        if (keep_e) x[i] = e;
+      }
     }
   } else {
-    for (int q = threadIdx.x; q < nvec; q += THREADS)
-      visit_sum(reinterpret_cast<const float4*>(mrow)[q], q * 4);
+    for (int q = threadIdx.x; q < nvec; q += THREADS) {
+      const float4 e = exp4(reinterpret_cast<const float4*>(mrow)[q], q * 4);
+      z += (e.x + e.y) + (e.z + e.w);
+    }
   }
   z = block_reduce<false>(z, sh);
 
@@ -115,17 +140,22 @@ k_softmax_rows(const float* __restrict__ M, int ldm, int V, PT* __restrict__ P, 
 
   float h = 0.f;
   PT* prow = P + (size_t)row * ldp;
-  auto emit = [&](const float4& v, int q) {
+  auto emit = [&](const float4& v, int q) {          // v = e (keep_e) or M
     const int c = q * 4;
-    float p0 = (c + 0 < V) ? softmax_prob(v.x, st) : 0.f;
-    float p1 = (c + 1 < V) ? softmax_prob(v.y, st) : 0.f;
-    float p2 = (c + 2 < V) ? softmax_prob(v.z, st) : 0.f;
-    float p3 = (c + 3 < V) ? softmax_prob(v.w, st) : 0.f;
-    if (want_entropy) {
-      if (c + 0 < V) h += p0 * ((v.x - mx) - st.log_z);
-      if (c + 1 < V) h += p1 * ((v.y - mx) - st.log_z);
-      if (c + 2 < V) h += p2 * ((v.z - mx) - st.log_z);
-      if (c + 3 < V) h += p3 * ((v.w - mx) - st.log_z);
+    float p0, p1, p2, p3;
+    if (keep_e) {
+      p0 = v.x * st.inv_z; p1 = v.y * st.inv_z; p2 = v.z * st.inv_z; p3 = v.w * st.inv_z;
+    } else {
+      p0 = (c + 0 < V) ? softmax_prob(v.x, st) : 0.f;
+      p1 = (c + 1 < V) ? softmax_prob(v.y, st) : 0.f;
+      p2 = (c + 2 < V) ? softmax_prob(v.z, st) : 0.f;
+      p3 = (c + 3 < V) ? softmax_prob(v.w, st) : 0.f;
+      if (want_entropy) {
+        if (c + 0 < V) h += p0 * ((v.x - mx) - st.log_z);
+        if (c + 1 < V) h += p1 * ((v.y - mx) - st.log_z);
+        if (c + 2 < V) h += p2 * ((v.z - mx) - st.log_z);
+        if (c + 3 < V) h += p3 * ((v.w - mx) - st.log_z);
+      }
     }
     if (P != nullptr) store_p4<PT>(prow + c, p0, p1, p2, p3);
     if (split.base != nullptr) store_split4(split, (size_t)row * ldp + c, p0, p1, p2, p3);

@@ -668,15 +668,21 @@ static int launch_softmax_rows(tgb200_mapper* h, cudaStream_t s, PT* P, int want
   if (nrows < 0) nrows = h->N - row0;
   const float* Mp = h->M.p + (size_t)row0 * h->ld;
   RowStat* st = h->stats.p + row0;
-  constexpr int TH = 256;
-#define SMX(ITEMS)                                                                                  \
-  k_softmax_rows<PT, TH, ITEMS><<<nrows, TH, 0, s>>>(Mp, h->ld, h->V, P, h->ld, st, rowaux, want_entropy, split)
-  if (nvec <= TH * 1) SMX(1);
-  else if (nvec <= TH * 2) SMX(2);
-  else if (nvec <= TH * 4) SMX(4);
-  else if (nvec <= TH * 8) SMX(8);
-  else if (nvec <= TH * 12) SMX(12);
-  else SMX(0);
+  // One CTA per row, the row cached in registers between the max / exp-sum / emit passes.  Wide rows use more threads with
+  // fewer float4 slots each: registers/thread stay <= 40..64, so 48-64 warps stay resident per SM (256 x 12 slots held 24,
+  // and the row pass was latency-bound at 0.46 of the HBM peak; profiles/README.md).  Rows wider than 6144 float4 re-read M.
+#define SMX(T, ITEMS, MINB)                                                                         \
+  k_softmax_rows<PT, T, ITEMS, MINB><<<nrows, T, 0, s>>>(Mp, h->ld, h->V, P, h->ld, st, rowaux, want_entropy, split)
+  if (nvec <= 256 * 1) SMX(256, 1, 1);
+  else if (nvec <= 256 * 2) SMX(256, 2, 1);
+  else if (nvec <= 256 * 4) SMX(256, 4, 1);
+  else if (nvec <= 512 * 3) SMX(512, 3, 3);
+  else if (nvec <= 512 * 4) SMX(512, 4, 3);
+  else if (nvec <= 512 * 5) SMX(512, 5, 3);
+  else if (nvec <= 1024 * 3) SMX(1024, 3, 2);
+  else if (nvec <= 1024 * 4) SMX(1024, 4, 1);
+  else if (nvec <= 1024 * 6) SMX(1024, 6, 1);
+  else SMX(1024, 0, 1);
 #undef SMX
   LAUNCH_CHECK("softmax_rows");
   return TGB200_OK;

@@ -204,6 +204,28 @@ def test_more_than_65535_voxels(precision):
     assert rel_fro(out, oo) < (5e-2 if precision == "bf16" else 1e-4)
 
 
+@pytest.mark.parametrize("V", [1030, 4100, 6150, 8190, 10000, 12290, 16390, 24570, 24580])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_row_pass_width_buckets(V, precision):
+    """The exact row pass (softmax over a row of M, one CTA per row) picks threads x register slots by row width: one V in each
+    bucket of launch_softmax_rows, both edges of the widest cached one, and the uncached path; entropy term on (the pass that
+    recomputes) and off (the pass that keeps exp(M - max) in registers)."""
+    from tangram_b200 import Mapper
+    N, K = 9, 4
+    rng = np.random.default_rng(V)
+    S = (rng.random((N, K)) + 0.1).astype(np.float32)
+    G = (rng.random((V, K)) + 0.1).astype(np.float32)
+    d = (G.sum(axis=1) / G.sum()).astype(np.float32)
+    M0 = (3.0 * rng.standard_normal((N, V))).astype(np.float32)
+    for lam_r in (0.0, 1e-2):
+        kw = dict(S=S, G=G, d=d, lambda_d=1.0, lambda_r=lam_r, lambda_l2=1e-6)
+        oo, oh = OracleMapper(M0=M0, **kw).train(2, print_each=None)
+        out, hist = Mapper(M0=M0, device="cuda:0", precision=precision, **kw).train(2, print_each=None)
+        assert np.allclose(out.sum(axis=1), 1.0, atol=1e-5)
+        assert max_rel([float(x) for x in hist["total_loss"]], [float(x) for x in oh["total_loss"]]) < (2e-3 if precision == "bf16" else 2e-5)
+        assert rel_fro(out, oo) < (5e-2 if precision == "bf16" else 1e-4)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 def test_manual_exchange_protocol_two_shards_on_one_gpu(precision):
     """The C-ABI's caller-driven sharded loop (tgb200_step_begin -> all-reduce of the exchange buffer -> tgb200_step_end):
